@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract: see the task's bench section).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision fp32|bf16]
+
+A "step" is one supervised autoencoder training step (NB:2676-2684: forward, alpha*MSE + CE, backward,
+Adam) over one batch of synthetic 3x64x64 images: BASELINE.json configs[1] (batch 256, fp32, 1 B200).
+With N > 1 GPUs every rank runs the same per-rank batch (weak scaling) and the flat gradient buffer is
+sum-allreduced once per step inside the captured step graph.
+
+value : whole-job images/s with the batches already resident in HBM (rotating over more batches than fit
+        in L2), device-timed with CUDA events, max over ranks.
+e2e   : the same metric through the public API with HOST (pinned) batches: H2D copy of every batch and a
+        D2H read of every step's loss inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+ALPHA, LR = 35.0, 5e-3          # the reference's best configuration (NB:2618)
+FLOP_PER_IMAGE_TRAIN = 181.9e6
+METRIC = "train images/sec (64x64x3, AE+MLP step)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return dict(hbm=float(d["hbm_gbs"]), tf=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                        tf_burst=float(d["bf16_tflops"]), source="measured")
+        except Exception:
+            pass
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_batches(n_batches, batch, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.rand(batch, 3, 64, 64, generator=g) for _ in range(n_batches)]
+    ys = [torch.randint(0, 10, (batch,), generator=g) for _ in range(n_batches)]
+    if pin:
+        xs = [x.pin_memory() for x in xs]
+        ys = [y.pin_memory() for y in ys]
+    return xs, ys
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference loop body on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_train_steps(batch, steps, warmup):
+    from oracle import seeded, torch_port as tp
+    torch.manual_seed(0)
+    st = seeded.seeded_state(seeded.ae_state_shapes(64, 10), 0)
+    x = torch.rand(batch, 3, 64, 64)
+    y = torch.randint(0, 10, (batch,))
+    opt = {}
+    for _ in range(warmup):
+        tp.ae_train_step(st, opt, x, y, ALPHA, LR)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tp.ae_train_step(st, opt, x, y, ALPHA, LR)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    steps = max(1, min(args.steps, 40))
+    ips, per = cpu_train_steps(args.batch, steps, max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "supervised AE train step (alpha*MSE + CE, Adam), batch 256, 3x64x64, latent 64",
+                   "batch_per_step": args.batch},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} train steps of batch {args.batch} (oracle/torch_port.py, torch CPU fp32)"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import ae_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = ae_b200.dp.init_communicator()
+    B = args.batch
+    torch.manual_seed(0)
+    model = ae_b200.SupervisedAutoencoder(64, 10, precision=args.precision, backend=args.backend).to(dev).train()
+    model.engine().prepare(dev, B)
+    if world > 1:
+        ae_b200.dp.broadcast_parameters(model)
+        model.engine().pack()
+    opt = ae_b200.Adam(model.parameters(), lr=LR)
+    stepper = ae_b200.TrainStep(model, opt, ALPHA, B, comm=comm)
+
+    n_rot = 12   # 12 x 12.6 MB of inputs > 126 MB of L2: every step reads a batch that is not L2-resident
+    xs_h, ys_h = synthetic_batches(n_rot, B, 1234 + rank, pin=True)
+    xs_d = [x.to(dev) for x in xs_h]
+    ys_d = [y.to(dev) for y in ys_h]
+    stream = stepper.stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def device_steps(k, i0=0):
+        for i in range(k):
+            stepper.load(xs_d[(i0 + i) % n_rot], ys_d[(i0 + i) % n_rot])
+            stepper.run()
+
+    # ---- device-resident throughput ----
+    device_steps(args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    device_steps(args.steps, args.warmup)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * args.steps / (ms * 1e-3)
+    final_loss = [float(v) for v in stepper.loss[:3].cpu()]
+
+    # ---- end to end: pinned host batches in, loss out, every step ----
+    loss_host = torch.zeros(4).pin_memory()
+    losses = []
+
+    def e2e_steps(k, i0=0):
+        for i in range(k):
+            stepper.load(xs_h[(i0 + i) % n_rot], ys_h[(i0 + i) % n_rot])
+            stepper.run()
+            with torch.cuda.stream(stream):
+                loss_host.copy_(stepper.loss, non_blocking=True)
+            stream.synchronize()
+            losses.append(float(loss_host[0]))
+
+    e2e_steps(min(args.warmup, 3))
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    w0 = time.perf_counter()
+    e2e_steps(args.steps)
+    t1.record(stream)
+    barrier()
+    wall = time.perf_counter() - w0
+    tt = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e = B * world * args.steps / float(tt.item())
+
+    peaks = measured_peaks()
+    flops = FLOP_PER_IMAGE_TRAIN * B
+    step_s = ms * 1e-3 / args.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": "supervised AE train step (alpha*MSE + CE, Adam), batch 256 per GPU, 3x64x64, latent 64",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "precision_mode": ("fp32 storage, tcgen05 2-term bf16 operand split, fp32 accumulate" if args.precision == "fp32"
+                                      else "bf16 operands, fp32 accumulate") if args.backend == "tc" else "fp32 CUDA cores",
+                   "backend": args.backend, "l2": f"inputs rotate over {n_rot} batches ({n_rot * B * 49152 / 1e6:.0f} MB > L2)",
+                   "final_loss": final_loss},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * (49152 + 8), "d2h_bytes_per_step": 16},
+        "gpu_launches": int(stepper.num_kernels) * args.steps,
+        "kernels_per_step": int(stepper.num_kernels),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": flops / step_s / 1e12, "peak": peaks["tf"], "unit": "TFLOP/s",
+                     "frac": flops / step_s / 1e12 / peaks["tf"], "traffic": None, "peak_source": peaks["source"],
+                     "scope": "whole step (181.9 MFLOP/image x batch / step time)"},
+    }
+    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        n = 12
+        ips, per = cpu_train_steps(B, n, 2)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{n} train steps of batch {B} (oracle/torch_port.py, torch CPU fp32)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        comm.close()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--precision", default=os.environ.get("AE_B200_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--backend", default=os.environ.get("AE_B200_BACKEND", "tc"), choices=["tc", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,13 @@
+"""B200-native supervised autoencoder + MLP hot path (drop-in for the reference notebook's modules).
+
+    from ae_b200 import Encoder, Decoder, SupervisedAutoencoder, MLP, Adam, TrainStep
+"""
+from . import _lib
+from .modules import Encoder, Decoder, SupervisedAutoencoder, MLP, default_backend, default_precision
+from .optim import Adam
+from .train import TrainStep
+from . import dp
+from .pipeline import extract_features, encode_predict
+
+__all__ = ["Encoder", "Decoder", "SupervisedAutoencoder", "MLP", "Adam", "TrainStep", "dp", "extract_features",
+           "encode_predict", "default_backend", "default_precision"]

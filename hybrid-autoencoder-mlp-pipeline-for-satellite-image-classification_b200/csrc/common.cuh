@@ -1,0 +1,204 @@
+// Shared internal declarations of libae_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/ae_b200.h"
+
+namespace ae {
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define AE_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ae::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+
+#define AE_CHECK(cond, ...)            \
+  do {                                 \
+    if (!(cond)) {                     \
+      ae::set_error(__VA_ARGS__);      \
+      return 1;                        \
+    }                                  \
+  } while (0)
+
+#define AE_TRY(expr)        \
+  do {                      \
+    int _r = (expr);        \
+    if (_r != 0) return _r; \
+  } while (0)
+
+#define AE_LAUNCH_CHECK()                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      ae::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return 1;                                                                             \
+    }                                                                                       \
+  } while (0)
+
+// ---- device-side descriptors ------------------------------------------------------------------
+struct Operand {
+  const float* src;
+  const float* src2;
+  const float* bnc;  // [AE_BNC_ROWS][C]
+  float scalar;
+  int mode;          // AE_OP_*
+  int C;             // channel count the coefficient block is indexed by (channel = k % C)
+};
+
+struct Epilogue {
+  int mode;          // AE_EPI_*
+  const float* bias;
+  const float* y;
+  const float* bnc;
+  double* stats;
+  int C;             // channels of the BN this epilogue feeds (channel = n % C)
+};
+
+struct Geom {
+  int B, Hs, Ws, Cb, Cs;
+  int lHs, lWs;      // log2
+};
+
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+inline Operand make_operand(const ae_operand_t* o, int C) {
+  Operand r;
+  r.src = o->src; r.src2 = o->src2; r.bnc = o->bnc; r.scalar = o->scalar; r.mode = o->mode; r.C = C;
+  return r;
+}
+inline Operand raw_operand(const float* p) {
+  Operand r; r.src = p; r.src2 = nullptr; r.bnc = nullptr; r.scalar = 0.f; r.mode = AE_OP_RAW; r.C = 1;
+  return r;
+}
+inline Operand bnrelu_operand(const float* y, const float* bnc, int C) {
+  Operand r; r.src = y; r.src2 = nullptr; r.bnc = bnc; r.scalar = 0.f; r.mode = AE_OP_BNRELU; r.C = C;
+  return r;
+}
+inline Operand bnbwd_operand(const float* dz, const float* y, const float* bnc, int C) {
+  Operand r; r.src = dz; r.src2 = y; r.bnc = bnc; r.scalar = 0.f; r.mode = AE_OP_BNBWD; r.C = C;
+  return r;
+}
+inline Epilogue make_epilogue(const ae_epilogue_t* e, int C) {
+  Epilogue r;
+  if (!e) { r.mode = AE_EPI_STORE; r.bias = nullptr; r.y = nullptr; r.bnc = nullptr; r.stats = nullptr; r.C = C; return r; }
+  r.mode = e->mode; r.bias = e->bias; r.y = e->y; r.bnc = e->bnc; r.stats = e->stats; r.C = C;
+  return r;
+}
+inline Epilogue store_epilogue(const float* bias = nullptr) {
+  Epilogue r; r.mode = AE_EPI_STORE; r.bias = bias; r.y = nullptr; r.bnc = nullptr; r.stats = nullptr; r.C = 1;
+  return r;
+}
+inline Epilogue bias_stats_epilogue(const float* bias, double* stats, int C) {
+  Epilogue r; r.mode = AE_EPI_BIAS_STATS; r.bias = bias; r.y = nullptr; r.bnc = nullptr; r.stats = stats; r.C = C;
+  return r;
+}
+inline Epilogue relubwd_epilogue(const float* y, const float* bnc, double* stats, int C) {
+  Epilogue r; r.mode = AE_EPI_RELUBWD_STATS; r.bias = nullptr; r.y = y; r.bnc = bnc; r.stats = stats; r.C = C;
+  return r;
+}
+
+#ifdef __CUDACC__
+// Load 4 consecutive channels [c, c+4) of an activation operand at element offset `off`
+// (off and c are multiples of 4) and apply the operand transform.  Invalid (padding) -> 0.
+__device__ __forceinline__ float4 load_operand4(const Operand& op, size_t off, int c, bool valid) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!valid) return v;
+  v = __ldg(reinterpret_cast<const float4*>(op.src + off));
+  if (op.mode == AE_OP_RAW) return v;
+  if (op.mode == AE_OP_BNRELU) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_SCALE * op.C + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_SHIFT * op.C + c));
+    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+    return v;
+  }
+  // AE_OP_BNBWD
+  const float4 y = __ldg(reinterpret_cast<const float4*>(op.src2 + off));
+  const float4 a = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_A * op.C + c));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_B * op.C + c));
+  const float4 k = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_C * op.C + c));
+  v.x = fmaf(a.x, v.x, fmaf(b.x, y.x, k.x));
+  v.y = fmaf(a.y, v.y, fmaf(b.y, y.y, k.y));
+  v.z = fmaf(a.z, v.z, fmaf(b.z, y.z, k.z));
+  v.w = fmaf(a.w, v.w, fmaf(b.w, y.w, k.w));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
+
+// ---- internal launchers (implemented across the .cu files) ---------------------------------------
+enum { FAM_DENSE = 0, FAM_FPROP = 1, FAM_DGRAD = 2 };
+
+// C[m][n] = sum_k A(m,k) * Bp[k][n]; Bp row-major fp32 [K][N] (for FAM_DGRAD: 4 phase blocks stacked, 9*Cs rows)
+struct RowGemm {
+  int family;
+  Geom g;
+  int M, N, K;       // FAM_DGRAD: M = B*Hs*Ws rows per phase, K is per phase (derived), N = Cb
+  Operand A;
+  const float* Bp;
+  Epilogue epi;
+  float* out;
+  int splitK;        // >1: partial[s][M][N] written instead of out (no bias / stats), DENSE/FPROP only
+  float* partial;
+};
+int simt_rowgemm(const RowGemm& p, cudaStream_t st);
+
+// C[i][j] = sum_m A(m,i) * B(m,j), m in [0,M): reduction over rows.
+struct ColGemm {
+  int gather;        // 0: A dense [M][I]; 1: A(m, i=(tap,cb)) gathered from the big image around small pixel m
+  Geom g;
+  int M, I, J;
+  Operand A, B;
+  float* out;        // final layout
+  int permC, permHW; // i' = (i % permC) * permHW + i / permC when permC > 0
+  int transposed;    // 0: out[i'*J + j]; 1: out[j*I + i']
+  int splitK;
+  float* partial;    // [splitK][I*J] in final layout order
+};
+int simt_colgemm(const ColGemm& p, cudaStream_t st);
+int colgemm_default_split(int M, int I, int J);
+
+// out[idx] = sum_s partial[s*n + idx] (+ bias[idx % bias_n]) (+ addend[idx])
+int reduce_partials(const float* partial, int splits, int64_t n, const float* bias, int bias_n,
+                    const float* addend, float* out, cudaStream_t st);
+// db[perm(n)] = sum_m a[m][n]
+int column_sums(const float* a, int M, int N, int permC, int permHW, float* out, cudaStream_t st);
+
+// fp32 [K][N] packs for the SIMT path
+int pack_conv_simt(const float* w, int Cs, int Cb, float* fwd, float* dgrad, cudaStream_t st);
+// generic permuted transpose: dst[r][c] from torch-layout linear weight (see dense.cu)
+int pack_linear(const float* w, int N, int K, int permC, int permHW, int kind, float* dst, cudaStream_t st);
+int permute_vector(const float* src, int n, int permC, int permHW, float* dst, cudaStream_t st);
+
+// tcgen05 path (tc_gemm.cu)
+size_t tc_packed_bytes(int Cs, int Cb, int nsplit);
+int tc_pack_conv(const float* w, int Cs, int Cb, int nsplit, void* fwd, void* dgrad, cudaStream_t st);
+int tc_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);
+int tc_wgrad(const ColGemm& p, int nsplit, cudaStream_t st);
+bool tc_rowgemm_supported(const RowGemm& p);
+
+}  // namespace ae

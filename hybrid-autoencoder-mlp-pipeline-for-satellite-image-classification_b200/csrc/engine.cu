@@ -1,0 +1,722 @@
+// Engine: orchestrates the kernels of the supervised autoencoder (NB:685-702) over caller-owned flat
+// parameter / gradient buffers and one caller-owned workspace.  Host-side only; every launch goes to the
+// stream the caller passes, so whole steps can be captured in a CUDA graph (ae_step_graph_*).
+#include <vector>
+
+#include "common.cuh"
+
+namespace ae {
+
+// defined in the other translation units
+int thin_gather_fwd(const Operand& thin, const float* w, const Epilogue& epi, float* out, int batch, cudaStream_t st);
+int thin_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* bias, float* x_hat, const float* x,
+                             double* sse, int batch, cudaStream_t st);
+int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes,
+               int batch, cudaStream_t st);
+size_t thin_wgrad_workspace_bytes(int batch);
+int bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float* rmean, float* rvar,
+                float* bnc, int C, int training, cudaStream_t st);
+int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta, int C,
+                  cudaStream_t st);
+int softmax_ce(const float* logits, const int64_t* labels, int B, int C, float gscale, float* loss, float* dlogits,
+               int* correct, const double* sse, double numel, float alpha, cudaStream_t st);
+int adam_step_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                   float wd, float gscale, int* step_dev, cudaStream_t st);
+int head_out(const float* hid_pre, const float* w2, const float* b2, float* logits, int B, int H, int C, cudaStream_t st);
+int head_backward_small(const float* dlogits, const float* w2, const float* hid_pre, float* dhid, float* dw2, float* db2,
+                        int B, int H, int C, cudaStream_t st);
+
+__global__ void k_inc_i64(int64_t* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += 1;
+}
+
+static inline int64_t pad4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+
+struct Tensor { int64_t off, size; };
+
+struct MidLayer {   // one of the six 32..256-channel stride-2 layers
+  Geom g;
+  int w, b;         // tensor indices inside the part
+  void* pk_fwd = nullptr;
+  void* pk_dgrad = nullptr;
+  size_t pk_bytes = 0;
+};
+
+struct BN {
+  int C;
+  int gamma, beta;  // tensor indices
+  int64_t count_per_image;
+  float* bnc = nullptr;
+  double* stats_f = nullptr;
+  double* stats_b = nullptr;
+};
+
+struct Part {
+  std::vector<Tensor> t;
+  int64_t flat_len = 0;
+  float* params = nullptr;
+  float* grads = nullptr;
+  float* running = nullptr;
+  int64_t* steps = nullptr;
+  std::vector<BN> bn;
+  std::vector<int64_t> run_off;  // offset of (mean, var) pair start per BN layer inside `running`
+  void add(int64_t size) { t.push_back({flat_len, size}); flat_len += pad4(size); }
+  float* P(int i) const { return params + t[i].off; }
+  float* G(int i) const { return grads + t[i].off; }
+  float* rmean(int l) const { return running ? running + run_off[l] : nullptr; }
+  float* rvar(int l) const { return running ? running + run_off[l] + bn[l].C : nullptr; }
+};
+
+}  // namespace ae
+
+using namespace ae;
+
+struct ae_engine {
+  ae_engine_config_t cfg;
+  int L, NC, Bmax;
+  bool simt;
+  int nsplit;             // bf16 operand split terms of the tcgen05 path
+  Part part[AE_NUM_PARTS];
+  MidLayer enc_mid[3];    // conv2..conv4
+  MidLayer dec_mid[3];    // convT1..convT3
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0, ws_need = 0;
+  // activations
+  float *y[4] = {}, *dzy[4] = {};     // encoder raw conv outputs / masked gradients
+  float *h = nullptr, *dh = nullptr;  // decoder_input output [B,4,4,256] NHWC and its gradient
+  float *t[3] = {}, *dzt[3] = {};     // decoder raw convT outputs / masked gradients
+  float *xhat = nullptr;
+  float *z = nullptr, *dz_dec = nullptr, *dz_head = nullptr, *dz_tot = nullptr;
+  float *hid_pre = nullptr, *dhid = nullptr, *logits = nullptr, *dlogits = nullptr;
+  // packs
+  float *encfc_fwd = nullptr, *encfc_bwd = nullptr, *decfc_fwd = nullptr, *decfc_bwd = nullptr, *decfc_bias = nullptr;
+  float *head_w1t = nullptr;
+  // scratch
+  float* partial = nullptr;
+  size_t partial_bytes = 0;
+  double* sse = nullptr;
+  double* stats_base = nullptr;
+  size_t stats_bytes = 0;
+  int fc_split = 16;
+  // pointers remembered between forward and backward
+  const float* last_x = nullptr;
+  const float* last_z_dec = nullptr;
+  const float* last_z_head = nullptr;
+  int last_batch = 0;
+};
+
+static void build_layouts(ae_engine* e) {
+  const int L = e->L, NC = e->NC;
+  Part& E = e->part[AE_PART_ENC];
+  const int ch[5] = {3, 32, 64, 128, 256};
+  int hw = 32;
+  for (int i = 0; i < 4; ++i) {
+    E.add((int64_t)ch[i + 1] * ch[i] * 9);  // conv weight
+    E.add(ch[i + 1]);                       // conv bias
+    E.add(ch[i + 1]);                       // bn gamma
+    E.add(ch[i + 1]);                       // bn beta
+    BN b; b.C = ch[i + 1]; b.gamma = 4 * i + 2; b.beta = 4 * i + 3; b.count_per_image = (int64_t)hw * hw;
+    E.bn.push_back(b);
+    hw /= 2;
+  }
+  E.add((int64_t)L * 4096);
+  E.add(L);
+  Part& D = e->part[AE_PART_DEC];
+  D.add((int64_t)4096 * L);
+  D.add(4096);
+  const int dch[5] = {256, 128, 64, 32, 3};
+  hw = 8;
+  for (int i = 0; i < 4; ++i) {
+    D.add((int64_t)dch[i] * dch[i + 1] * 9);
+    D.add(dch[i + 1]);
+    if (i < 3) {
+      D.add(dch[i + 1]);
+      D.add(dch[i + 1]);
+      BN b; b.C = dch[i + 1]; b.gamma = 2 + 4 * i + 2; b.beta = 2 + 4 * i + 3; b.count_per_image = (int64_t)hw * hw;
+      D.bn.push_back(b);
+      hw *= 2;
+    }
+  }
+  Part& H = e->part[AE_PART_HEAD];
+  H.add((int64_t)128 * L);
+  H.add(128);
+  H.add((int64_t)NC * 128);
+  H.add(NC);
+  for (int p = 0; p < AE_NUM_PARTS; ++p) {
+    int64_t off = 0;
+    for (auto& b : e->part[p].bn) { e->part[p].run_off.push_back(off); off += 2 * b.C; }
+  }
+  // mid layers: encoder conv2..4 (big -> small), decoder convT1..3 (small -> big)
+  const int ehs[3] = {16, 8, 4};
+  for (int i = 0; i < 3; ++i) {
+    MidLayer& m = e->enc_mid[i];
+    m.g.B = 0; m.g.Hs = ehs[i]; m.g.Ws = ehs[i]; m.g.Cb = ch[i + 1]; m.g.Cs = ch[i + 2];
+    m.g.lHs = ilog2(ehs[i]); m.g.lWs = m.g.lHs;
+    m.w = 4 * (i + 1); m.b = 4 * (i + 1) + 1;
+  }
+  const int dhs[3] = {4, 8, 16};
+  for (int i = 0; i < 3; ++i) {
+    MidLayer& m = e->dec_mid[i];
+    m.g.B = 0; m.g.Hs = dhs[i]; m.g.Ws = dhs[i]; m.g.Cs = dch[i]; m.g.Cb = dch[i + 1];
+    m.g.lHs = ilog2(dhs[i]); m.g.lWs = m.g.lHs;
+    m.w = 2 + 4 * i; m.b = 2 + 4 * i + 1;
+  }
+}
+
+// Carve the workspace.  Called with base == nullptr to measure.
+static size_t carve(ae_engine* e, char* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> char* {
+    off = (off + 255) & ~(size_t)255;
+    char* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  };
+  const size_t B = (size_t)e->Bmax;
+  const int L = e->L, NC = e->NC;
+  const size_t ysz[4] = {B * 32 * 32 * 32, B * 16 * 16 * 64, B * 8 * 8 * 128, B * 4 * 4 * 256};
+  for (int i = 0; i < 4; ++i) e->y[i] = (float*)take(ysz[i] * 4);
+  for (int i = 0; i < 4; ++i) e->dzy[i] = (float*)take(ysz[i] * 4);
+  e->h = (float*)take(B * 4096 * 4);
+  e->dh = (float*)take(B * 4096 * 4);
+  const size_t tsz[3] = {B * 8 * 8 * 128, B * 16 * 16 * 64, B * 32 * 32 * 32};
+  for (int i = 0; i < 3; ++i) e->t[i] = (float*)take(tsz[i] * 4);
+  for (int i = 0; i < 3; ++i) e->dzt[i] = (float*)take(tsz[i] * 4);
+  e->xhat = (float*)take(B * 3 * 64 * 64 * 4);
+  e->z = (float*)take(B * L * 4);
+  e->dz_dec = (float*)take(B * L * 4);
+  e->dz_head = (float*)take(B * L * 4);
+  e->dz_tot = (float*)take(B * L * 4);
+  e->hid_pre = (float*)take(B * 128 * 4);
+  e->dhid = (float*)take(B * 128 * 4);
+  e->logits = (float*)take(B * (size_t)pad4(NC) * 4);
+  e->dlogits = (float*)take(B * (size_t)pad4(NC) * 4);
+  // BN coefficient blocks and statistics
+  char* stats0 = nullptr;
+  size_t stats_begin = 0;
+  for (int p = 0; p < 2; ++p)
+    for (auto& b : e->part[p].bn) b.bnc = (float*)take((size_t)AE_BNC_ROWS * b.C * 4);
+  off = (off + 255) & ~(size_t)255;
+  stats_begin = off;
+  stats0 = base ? base + off : nullptr;
+  for (int p = 0; p < 2; ++p)
+    for (auto& b : e->part[p].bn) {
+      b.stats_f = (double*)(base ? base + off : nullptr); off += (size_t)2 * b.C * 8;
+      b.stats_b = (double*)(base ? base + off : nullptr); off += (size_t)2 * b.C * 8;
+    }
+  e->sse = (double*)(base ? base + off : nullptr); off += 16;
+  e->stats_base = (double*)stats0;
+  e->stats_bytes = off - stats_begin;
+  // packed weights
+  for (int i = 0; i < 3; ++i) {
+    for (MidLayer* m : {&e->enc_mid[i], &e->dec_mid[i]}) {
+      const size_t bytes = e->simt ? (size_t)9 * m->g.Cb * m->g.Cs * 4 : tc_packed_bytes(m->g.Cs, m->g.Cb, e->nsplit);
+      m->pk_bytes = bytes;
+      m->pk_fwd = take(bytes);
+      m->pk_dgrad = take(bytes);
+    }
+  }
+  e->encfc_fwd = (float*)take((size_t)4096 * L * 4);
+  e->encfc_bwd = (float*)take((size_t)4096 * L * 4);
+  e->decfc_fwd = (float*)take((size_t)4096 * L * 4);
+  e->decfc_bwd = (float*)take((size_t)4096 * L * 4);
+  e->decfc_bias = (float*)take(4096 * 4);
+  e->head_w1t = (float*)take((size_t)128 * L * 4);
+  // split-K / weight-gradient partial buffer
+  size_t pb = 0;
+  auto upd = [&](size_t v) { if (v > pb) pb = v; };
+  for (int i = 0; i < 3; ++i)
+    for (MidLayer* m : {&e->enc_mid[i], &e->dec_mid[i]}) {
+      const int I = 9 * m->g.Cb, J = m->g.Cs;
+      const int Mrows = (int)(B * m->g.Hs * m->g.Ws);
+      upd((size_t)colgemm_default_split(Mrows, I, J) * I * J * 4);
+    }
+  upd((size_t)colgemm_default_split((int)B, 4096, L) * 4096 * L * 4);
+  upd((size_t)colgemm_default_split((int)B, 128, L) * 128 * L * 4);
+  upd((size_t)e->fc_split * B * L * 4);
+  upd(thin_wgrad_workspace_bytes((int)B));
+  e->partial_bytes = pb;
+  e->partial = (float*)take(pb);
+  return off + 256;
+}
+
+static int check_batch(const ae_engine* e, int batch) {
+  AE_CHECK(e->ws != nullptr, "engine: workspace not bound (ae_engine_bind_workspace)");
+  AE_CHECK(batch >= 1 && batch <= e->Bmax, "engine: batch %d outside [1, max_batch=%d]", batch, e->Bmax);
+  return 0;
+}
+static int check_part(const ae_engine* e, int p, bool need_grads) {
+  AE_CHECK(e->part[p].params != nullptr, "engine: part %d has no parameters bound (ae_engine_bind_part)", p);
+  AE_CHECK(!need_grads || e->part[p].grads != nullptr, "engine: part %d has no gradient buffer bound", p);
+  return 0;
+}
+
+static int run_rowgemm(ae_engine* e, RowGemm& r, const void* pk_tc, cudaStream_t st) {
+  if (!e->simt && pk_tc != nullptr && tc_rowgemm_supported(r)) return tc_rowgemm(r, pk_tc, e->nsplit, st);
+  return simt_rowgemm(r, st);
+}
+
+static int run_wgrad(ae_engine* e, ColGemm& c, cudaStream_t st) {
+  c.splitK = colgemm_default_split(c.M, c.I, c.J);
+  c.partial = e->partial;
+  AE_CHECK((size_t)c.splitK * c.I * c.J * 4 <= e->partial_bytes, "engine: partial buffer too small");
+  if (!e->simt && c.gather) return tc_wgrad(c, e->nsplit, st);
+  return simt_colgemm(c, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int ae_engine_create(const ae_engine_config_t* cfg, ae_engine_t** out) {
+  AE_CHECK(cfg && out, "ae_engine_create: null argument");
+  AE_CHECK(cfg->latent_dim >= 16 && cfg->latent_dim % 16 == 0 && cfg->latent_dim <= 1024,
+           "ae_engine_create: latent_dim=%d must be a multiple of 16 in [16,1024]", cfg->latent_dim);
+  AE_CHECK(cfg->num_classes >= 2 && cfg->num_classes <= 64, "ae_engine_create: num_classes=%d out of range", cfg->num_classes);
+  AE_CHECK(cfg->max_batch >= 1, "ae_engine_create: max_batch must be >= 1");
+  AE_CHECK(cfg->precision == AE_PREC_FP32 || cfg->precision == AE_PREC_BF16, "ae_engine_create: bad precision");
+  AE_CHECK(cfg->backend == AE_BACKEND_TC || cfg->backend == AE_BACKEND_SIMT, "ae_engine_create: bad backend");
+  ae_engine* e = new ae_engine();
+  e->cfg = *cfg;
+  e->L = cfg->latent_dim; e->NC = cfg->num_classes; e->Bmax = cfg->max_batch;
+  e->simt = cfg->backend == AE_BACKEND_SIMT;
+  e->nsplit = cfg->precision == AE_PREC_FP32 ? 2 : 1;
+  build_layouts(e);
+  e->ws_need = carve(e, nullptr);
+  *out = e;
+  return 0;
+}
+
+void ae_engine_destroy(ae_engine_t* e) { delete e; }
+
+int ae_engine_param_layout(const ae_engine_t* e, int part, int64_t* offsets, int64_t* sizes, int64_t* flat_len) {
+  if (!e || part < 0 || part >= AE_NUM_PARTS) return -1;
+  const Part& p = e->part[part];
+  for (size_t i = 0; i < p.t.size(); ++i) {
+    if (offsets) offsets[i] = p.t[i].off;
+    if (sizes) sizes[i] = p.t[i].size;
+  }
+  if (flat_len) *flat_len = p.flat_len;
+  return (int)p.t.size();
+}
+
+int ae_engine_bn_layout(const ae_engine_t* e, int part, int* channels) {
+  if (!e || part < 0 || part >= AE_NUM_PARTS) return -1;
+  const Part& p = e->part[part];
+  for (size_t i = 0; i < p.bn.size(); ++i)
+    if (channels) channels[i] = p.bn[i].C;
+  return (int)p.bn.size();
+}
+
+size_t ae_engine_workspace_bytes(const ae_engine_t* e) { return e ? e->ws_need : 0; }
+
+int ae_engine_bind_workspace(ae_engine_t* e, void* workspace, size_t bytes) {
+  AE_CHECK(e && workspace, "ae_engine_bind_workspace: null argument");
+  AE_CHECK(bytes >= e->ws_need, "ae_engine_bind_workspace: %zu bytes given, %zu needed", bytes, e->ws_need);
+  AE_CHECK(((uintptr_t)workspace & 255) == 0, "ae_engine_bind_workspace: workspace must be 256-byte aligned");
+  e->ws = workspace; e->ws_bytes = bytes;
+  carve(e, static_cast<char*>(workspace));
+  return 0;
+}
+
+int ae_engine_bind_part(ae_engine_t* e, int part, float* params, float* grads, float* bn_running, int64_t* bn_steps) {
+  AE_CHECK(e && part >= 0 && part < AE_NUM_PARTS, "ae_engine_bind_part: bad part");
+  AE_CHECK(params != nullptr, "ae_engine_bind_part: params must not be null");
+  AE_CHECK((((uintptr_t)params | (uintptr_t)grads) & 15) == 0, "ae_engine_bind_part: buffers must be 16-byte aligned");
+  Part& p = e->part[part];
+  p.params = params; p.grads = grads; p.running = bn_running; p.steps = bn_steps;
+  return 0;
+}
+
+int ae_engine_pack_weights(ae_engine_t* e, int part, ae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AE_CHECK(e && e->ws, "ae_engine_pack_weights: workspace not bound");
+  AE_TRY(check_part(e, part, false));
+  const Part& p = e->part[part];
+  const int L = e->L;
+  if (part == AE_PART_ENC || part == AE_PART_DEC) {
+    MidLayer* mids = part == AE_PART_ENC ? e->enc_mid : e->dec_mid;
+    for (int i = 0; i < 3; ++i) {
+      MidLayer& m = mids[i];
+      if (e->simt) AE_TRY(pack_conv_simt(p.P(m.w), m.g.Cs, m.g.Cb, (float*)m.pk_fwd, (float*)m.pk_dgrad, st));
+      else AE_TRY(tc_pack_conv(p.P(m.w), m.g.Cs, m.g.Cb, e->nsplit, m.pk_fwd, m.pk_dgrad, st));
+    }
+  }
+  if (part == AE_PART_ENC) {
+    AE_TRY(pack_linear(p.P(16), L, 4096, 256, 16, 0, e->encfc_fwd, st));   // [4096 nhwc][L]
+    AE_TRY(pack_linear(p.P(16), L, 4096, 256, 16, 1, e->encfc_bwd, st));   // [L][4096 nhwc]
+  } else if (part == AE_PART_DEC) {
+    AE_TRY(pack_linear(p.P(0), 4096, L, 256, 16, 2, e->decfc_fwd, st));    // [L][4096 nhwc]
+    AE_TRY(pack_linear(p.P(0), 4096, L, 256, 16, 3, e->decfc_bwd, st));    // [4096 nhwc][L]
+    AE_TRY(permute_vector(p.P(1), 4096, 256, 16, e->decfc_bias, st));
+  } else {
+    AE_TRY(pack_linear(p.P(0), 128, L, 0, 0, 0, e->head_w1t, st));         // [L][128]
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Encoder (NB:499-525)
+// ---------------------------------------------------------------------------------------------
+int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, float* z, ae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AE_TRY(check_batch(e, batch));
+  AE_TRY(check_part(e, AE_PART_ENC, false));
+  Part& P = e->part[AE_PART_ENC];
+  AE_CHECK(!training || P.running, "ae_encoder_forward: training mode needs BatchNorm running buffers");
+  if (training) {
+    AE_CUDA(cudaMemsetAsync(P.bn[0].stats_f, 0, (char*)(P.bn[3].stats_b + 2 * P.bn[3].C) - (char*)P.bn[0].stats_f, st));
+    if (P.steps) { k_inc_i64<<<1, 32, 0, st>>>(P.steps, 4); AE_LAUNCH_CHECK(); }
+  }
+  // conv1 (3 -> 32): x NCHW fp32 -> y1 NHWC
+  {
+    Epilogue ep = training ? bias_stats_epilogue(P.P(1), P.bn[0].stats_f, 32) : store_epilogue(P.P(1));
+    ep.C = 32;
+    AE_TRY(thin_gather_fwd(raw_operand(x), P.P(0), ep, e->y[0], batch, st));
+    AE_TRY(bn_finalize(P.bn[0].stats_f, (int64_t)batch * 1024, P.P(2), P.P(3), P.rmean(0), P.rvar(0), P.bn[0].bnc, 32,
+                       training, st));
+  }
+  for (int i = 0; i < 3; ++i) {
+    MidLayer& m = e->enc_mid[i];
+    BN& bin = P.bn[i];
+    BN& bout = P.bn[i + 1];
+    RowGemm r{};
+    r.family = FAM_FPROP; r.g = m.g; r.g.B = batch;
+    r.M = batch * m.g.Hs * m.g.Ws; r.N = m.g.Cs; r.K = 9 * m.g.Cb;
+    r.A = bnrelu_operand(e->y[i], bin.bnc, bin.C);
+    r.Bp = (const float*)m.pk_fwd;
+    r.epi = training ? bias_stats_epilogue(P.P(m.b), bout.stats_f, bout.C) : store_epilogue(P.P(m.b));
+    r.epi.C = bout.C;
+    r.out = e->y[i + 1]; r.splitK = 1; r.partial = nullptr;
+    AE_TRY(run_rowgemm(e, r, m.pk_fwd, st));
+    AE_TRY(bn_finalize(bout.stats_f, (int64_t)batch * bout.count_per_image, P.P(bout.gamma), P.P(bout.beta),
+                       P.rmean(i + 1), P.rvar(i + 1), bout.bnc, bout.C, training, st));
+  }
+  {  // Flatten + Linear(4096, L): split-K partials, fixed-order reduce (+bias)
+    RowGemm r{};
+    r.family = FAM_DENSE; r.M = batch; r.N = e->L; r.K = 4096;
+    r.A = bnrelu_operand(e->y[3], P.bn[3].bnc, 256);
+    r.Bp = e->encfc_fwd; r.epi = store_epilogue(); r.out = nullptr;
+    r.splitK = e->fc_split; r.partial = e->partial;
+    AE_TRY(simt_rowgemm(r, st));
+    AE_TRY(reduce_partials(e->partial, e->fc_split, (int64_t)batch * e->L, P.P(17), e->L, nullptr, e->z, st));
+    if (z && z != e->z) AE_CUDA(cudaMemcpyAsync(z, e->z, (size_t)batch * e->L * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  e->last_x = x;
+  e->last_batch = batch;
+  return 0;
+}
+
+int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AE_TRY(check_batch(e, batch));
+  AE_TRY(check_part(e, AE_PART_ENC, true));
+  AE_CHECK(e->last_x != nullptr && e->last_batch == batch, "ae_encoder_backward: no matching training forward");
+  Part& P = e->part[AE_PART_ENC];
+  const int L = e->L;
+  {  // Linear(4096, L) backward
+    ColGemm c{};
+    c.gather = 0; c.M = batch; c.I = 4096; c.J = L;
+    c.A = bnrelu_operand(e->y[3], P.bn[3].bnc, 256);
+    c.B = raw_operand(dz);
+    c.out = P.G(16); c.permC = 256; c.permHW = 16; c.transposed = 1;
+    AE_TRY(run_wgrad(e, c, st));
+    AE_TRY(column_sums(dz, batch, L, 0, 0, P.G(17), st));
+    RowGemm r{};
+    r.family = FAM_DENSE; r.M = batch; r.N = 4096; r.K = L;
+    r.A = raw_operand(dz); r.Bp = e->encfc_bwd;
+    r.epi = relubwd_epilogue(e->y[3], P.bn[3].bnc, P.bn[3].stats_b, 256);
+    r.out = e->dzy[3]; r.splitK = 1;
+    AE_TRY(simt_rowgemm(r, st));
+    AE_TRY(bn_bwd_reduce(P.bn[3].stats_b, (int64_t)batch * 16, P.P(P.bn[3].gamma), P.bn[3].bnc, P.G(P.bn[3].gamma),
+                         P.G(P.bn[3].beta), 256, st));
+  }
+  for (int i = 2; i >= 0; --i) {
+    MidLayer& m = e->enc_mid[i];
+    BN& bin = P.bn[i];        // BN of this layer's input (big image)
+    BN& bout = P.bn[i + 1];   // BN of this layer's output (small image)
+    const int Mrows = batch * m.g.Hs * m.g.Ws;
+    ColGemm c{};
+    c.gather = 1; c.g = m.g; c.g.B = batch; c.M = Mrows; c.I = 9 * m.g.Cb; c.J = m.g.Cs;
+    c.A = bnrelu_operand(e->y[i], bin.bnc, bin.C);
+    c.B = bnbwd_operand(e->dzy[i + 1], e->y[i + 1], bout.bnc, bout.C);
+    c.out = P.G(m.w); c.permC = m.g.Cb; c.permHW = 9; c.transposed = 1;
+    AE_TRY(run_wgrad(e, c, st));
+    AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cs * 4, st));   // bias feeding a training BN: exact zero gradient
+    RowGemm r{};
+    r.family = FAM_DGRAD; r.g = m.g; r.g.B = batch; r.M = Mrows; r.N = m.g.Cb; r.K = 0;
+    r.A = bnbwd_operand(e->dzy[i + 1], e->y[i + 1], bout.bnc, bout.C);
+    r.Bp = (const float*)m.pk_dgrad;
+    r.epi = relubwd_epilogue(e->y[i], bin.bnc, bin.stats_b, bin.C);
+    r.out = e->dzy[i]; r.splitK = 1;
+    AE_TRY(run_rowgemm(e, r, m.pk_dgrad, st));
+    AE_TRY(bn_bwd_reduce(bin.stats_b, (int64_t)batch * bin.count_per_image, P.P(bin.gamma), bin.bnc, P.G(bin.gamma),
+                         P.G(bin.beta), bin.C, st));
+  }
+  // conv1 weight gradient (no data gradient needed)
+  AE_TRY(thin_wgrad(bnbwd_operand(e->dzy[0], e->y[0], P.bn[0].bnc, 32), raw_operand(e->last_x), P.G(0), nullptr,
+                    e->partial, e->partial_bytes, batch, st));
+  AE_CUDA(cudaMemsetAsync(P.G(1), 0, 32 * 4, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder (NB:607-635)
+// ---------------------------------------------------------------------------------------------
+static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int training, float* x_hat, const float* x_target,
+                                cudaStream_t st) {
+  AE_TRY(check_batch(e, batch));
+  AE_TRY(check_part(e, AE_PART_DEC, false));
+  Part& P = e->part[AE_PART_DEC];
+  AE_CHECK(!training || P.running, "ae_decoder_forward: training mode needs BatchNorm running buffers");
+  if (training) {
+    AE_CUDA(cudaMemsetAsync(P.bn[0].stats_f, 0, (char*)(e->sse + 2) - (char*)P.bn[0].stats_f, st));
+    if (P.steps) { k_inc_i64<<<1, 32, 0, st>>>(P.steps, 3); AE_LAUNCH_CHECK(); }
+  } else {
+    AE_CUDA(cudaMemsetAsync(e->sse, 0, 16, st));
+  }
+  {  // decoder_input: Linear(L, 4096) + Unflatten, written NHWC
+    RowGemm r{};
+    r.family = FAM_DENSE; r.M = batch; r.N = 4096; r.K = e->L;
+    r.A = raw_operand(z); r.Bp = e->decfc_fwd; r.epi = store_epilogue(e->decfc_bias);
+    r.out = e->h; r.splitK = 1;
+    AE_TRY(simt_rowgemm(r, st));
+  }
+  for (int i = 0; i < 3; ++i) {
+    MidLayer& m = e->dec_mid[i];
+    BN& bout = P.bn[i];
+    RowGemm r{};
+    r.family = FAM_DGRAD; r.g = m.g; r.g.B = batch; r.M = batch * m.g.Hs * m.g.Ws; r.N = m.g.Cb; r.K = 0;
+    r.A = i == 0 ? raw_operand(e->h) : bnrelu_operand(e->t[i - 1], P.bn[i - 1].bnc, P.bn[i - 1].C);
+    if (i == 0) r.A.C = m.g.Cs;
+    r.Bp = (const float*)m.pk_dgrad;
+    r.epi = training ? bias_stats_epilogue(P.P(m.b), bout.stats_f, bout.C) : store_epilogue(P.P(m.b));
+    r.epi.C = bout.C;
+    r.out = e->t[i]; r.splitK = 1;
+    AE_TRY(run_rowgemm(e, r, m.pk_dgrad, st));
+    AE_TRY(bn_finalize(bout.stats_f, (int64_t)batch * bout.count_per_image, P.P(bout.gamma), P.P(bout.beta), P.rmean(i),
+                       P.rvar(i), bout.bnc, bout.C, training, st));
+  }
+  float* xo = x_hat ? x_hat : e->xhat;
+  AE_TRY(thin_scatter_sigmoid_fwd(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), P.P(14), P.P(15), xo, x_target, e->sse, batch, st));
+  if (x_hat && training) AE_CUDA(cudaMemcpyAsync(e->xhat, x_hat, (size_t)batch * 12288 * 4, cudaMemcpyDeviceToDevice, st));
+  e->last_z_dec = z;
+  e->last_batch = batch;
+  return 0;
+}
+
+int ae_decoder_forward(ae_engine_t* e, const float* z, int batch, int training, float* x_hat, ae_stream_t stream) {
+  return decoder_forward_impl(e, z, batch, training, x_hat, nullptr, (cudaStream_t)stream);
+}
+
+// thin_up: SIGMOID_BWD operand describing d(loss)/d(pre-sigmoid)
+static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int batch, float* dz, const float* dz_addend,
+                                 cudaStream_t st) {
+  AE_TRY(check_batch(e, batch));
+  AE_TRY(check_part(e, AE_PART_DEC, true));
+  AE_CHECK(e->last_z_dec != nullptr && e->last_batch == batch, "ae_decoder_backward: no matching training forward");
+  Part& P = e->part[AE_PART_DEC];
+  const int L = e->L;
+  // convT4 (32 -> 3)
+  AE_TRY(thin_wgrad(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), thin_up, P.G(14), P.G(15), e->partial, e->partial_bytes, batch, st));
+  AE_TRY(thin_gather_fwd(thin_up, P.P(14), relubwd_epilogue(e->t[2], P.bn[2].bnc, P.bn[2].stats_b, 32), e->dzt[2], batch, st));
+  AE_TRY(bn_bwd_reduce(P.bn[2].stats_b, (int64_t)batch * 1024, P.P(P.bn[2].gamma), P.bn[2].bnc, P.G(P.bn[2].gamma),
+                       P.G(P.bn[2].beta), 32, st));
+  for (int i = 2; i >= 0; --i) {
+    MidLayer& m = e->dec_mid[i];
+    BN& bout = P.bn[i];  // BN after this layer's output (big image)
+    const int Mrows = batch * m.g.Hs * m.g.Ws;
+    const Operand small = i == 0 ? raw_operand(e->h) : bnrelu_operand(e->t[i - 1], P.bn[i - 1].bnc, P.bn[i - 1].C);
+    ColGemm c{};
+    c.gather = 1; c.g = m.g; c.g.B = batch; c.M = Mrows; c.I = 9 * m.g.Cb; c.J = m.g.Cs;
+    c.A = bnbwd_operand(e->dzt[i], e->t[i], bout.bnc, bout.C);
+    c.B = small;
+    if (i == 0) c.B.C = m.g.Cs;
+    c.out = P.G(m.w); c.permC = m.g.Cb; c.permHW = 9; c.transposed = 1;
+    AE_TRY(run_wgrad(e, c, st));
+    AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cb * 4, st));
+    RowGemm r{};
+    r.family = FAM_FPROP; r.g = m.g; r.g.B = batch; r.M = Mrows; r.N = m.g.Cs; r.K = 9 * m.g.Cb;
+    r.A = bnbwd_operand(e->dzt[i], e->t[i], bout.bnc, bout.C);
+    r.Bp = (const float*)m.pk_fwd;
+    if (i == 0) { r.epi = store_epilogue(); r.epi.C = m.g.Cs; r.out = e->dh; }
+    else { BN& bin = P.bn[i - 1]; r.epi = relubwd_epilogue(e->t[i - 1], bin.bnc, bin.stats_b, bin.C); r.out = e->dzt[i - 1]; }
+    r.splitK = 1;
+    AE_TRY(run_rowgemm(e, r, m.pk_fwd, st));
+    if (i > 0) {
+      BN& bin = P.bn[i - 1];
+      AE_TRY(bn_bwd_reduce(bin.stats_b, (int64_t)batch * bin.count_per_image, P.P(bin.gamma), bin.bnc, P.G(bin.gamma),
+                           P.G(bin.beta), bin.C, st));
+    }
+  }
+  {  // decoder_input backward
+    ColGemm c{};
+    c.gather = 0; c.M = batch; c.I = 4096; c.J = L;
+    c.A = raw_operand(e->dh); c.B = raw_operand(e->last_z_dec);
+    c.out = P.G(0); c.permC = 256; c.permHW = 16; c.transposed = 0;
+    AE_TRY(run_wgrad(e, c, st));
+    AE_TRY(column_sums(e->dh, batch, 4096, 256, 16, P.G(1), st));
+    RowGemm r{};
+    r.family = FAM_DENSE; r.M = batch; r.N = L; r.K = 4096;
+    r.A = raw_operand(e->dh); r.Bp = e->decfc_bwd; r.epi = store_epilogue(); r.out = nullptr;
+    r.splitK = e->fc_split; r.partial = e->partial;
+    AE_TRY(simt_rowgemm(r, st));
+    AE_TRY(reduce_partials(e->partial, e->fc_split, (int64_t)batch * L, nullptr, 0, dz_addend, dz, st));
+  }
+  return 0;
+}
+
+int ae_decoder_backward(ae_engine_t* e, const float* d_xhat, int batch, float* dz, ae_stream_t stream) {
+  AE_CHECK(e && d_xhat && dz, "ae_decoder_backward: null argument");
+  Operand up;
+  up.src = d_xhat; up.src2 = e->xhat; up.bnc = nullptr; up.scalar = 0.f; up.mode = AE_OP_SIGMOID_BWD; up.C = 1;
+  return decoder_backward_impl(e, up, batch, dz, nullptr, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Classifier head (NB:692-696)
+// ---------------------------------------------------------------------------------------------
+int ae_head_forward(ae_engine_t* e, const float* z, int batch, float* logits, ae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AE_TRY(check_batch(e, batch));
+  AE_TRY(check_part(e, AE_PART_HEAD, false));
+  Part& P = e->part[AE_PART_HEAD];
+  RowGemm r{};
+  r.family = FAM_DENSE; r.M = batch; r.N = 128; r.K = e->L;
+  r.A = raw_operand(z); r.Bp = e->head_w1t; r.epi = store_epilogue(P.P(1)); r.out = e->hid_pre; r.splitK = 1;
+  AE_TRY(simt_rowgemm(r, st));
+  AE_TRY(head_out(e->hid_pre, P.P(2), P.P(3), logits ? logits : e->logits, batch, 128, e->NC, st));
+  e->last_z_head = z;
+  e->last_batch = batch;
+  return 0;
+}
+
+int ae_head_backward(ae_engine_t* e, const float* d_logits, int batch, float* dz, ae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AE_TRY(check_batch(e, batch));
+  AE_TRY(check_part(e, AE_PART_HEAD, true));
+  AE_CHECK(e->last_z_head != nullptr && e->last_batch == batch, "ae_head_backward: no matching forward");
+  Part& P = e->part[AE_PART_HEAD];
+  const int L = e->L;
+  AE_TRY(head_backward_small(d_logits, P.P(2), e->hid_pre, e->dhid, P.G(2), P.G(3), batch, 128, e->NC, st));
+  ColGemm c{};
+  c.gather = 0; c.M = batch; c.I = 128; c.J = L;
+  c.A = raw_operand(e->dhid); c.B = raw_operand(e->last_z_head);
+  c.out = P.G(0); c.permC = 0; c.permHW = 0; c.transposed = 0;
+  AE_TRY(run_wgrad(e, c, st));
+  AE_TRY(column_sums(e->dhid, batch, 128, 0, 0, P.G(1), st));
+  RowGemm r{};
+  r.family = FAM_DENSE; r.M = batch; r.N = L; r.K = 128;
+  r.A = raw_operand(e->dhid); r.Bp = P.P(0); r.epi = store_epilogue(); r.out = dz; r.splitK = 1;
+  AE_TRY(simt_rowgemm(r, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused supervised step (NB:2676-2683 without the optimizer) and evaluation (NB:2694-2714)
+// ---------------------------------------------------------------------------------------------
+int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int batch, float alpha, float* loss_out,
+                  ae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AE_CHECK(e && x && labels && loss_out, "ae_train_step: null argument");
+  AE_TRY(ae_encoder_forward(e, x, batch, 1, nullptr, stream));
+  AE_TRY(decoder_forward_impl(e, e->z, batch, 1, nullptr, x, st));
+  AE_TRY(ae_head_forward(e, e->z, batch, nullptr, stream));
+  const double numel = (double)batch * 12288.0;
+  AE_TRY(softmax_ce(e->logits, labels, batch, e->NC, 1.f, loss_out, e->dlogits, nullptr, e->sse, numel, alpha, st));
+  AE_TRY(ae_head_backward(e, e->dlogits, batch, e->dz_head, stream));
+  Operand up;
+  up.src = x; up.src2 = e->xhat; up.bnc = nullptr; up.scalar = (float)(2.0 * (double)alpha / numel);
+  up.mode = AE_OP_SIGMOID_BWD; up.C = 1;
+  AE_TRY(decoder_backward_impl(e, up, batch, e->dz_tot, e->dz_head, st));
+  AE_TRY(ae_encoder_backward(e, e->dz_tot, batch, stream));
+  return 0;
+}
+
+int ae_eval_step(ae_engine_t* e, const float* x, const int64_t* labels, int batch, float alpha, float* loss_out,
+                 float* x_hat, float* logits, float* z, ae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AE_CHECK(e && x, "ae_eval_step: null argument");
+  AE_TRY(ae_encoder_forward(e, x, batch, 0, z, stream));
+  AE_TRY(decoder_forward_impl(e, e->z, batch, 0, x_hat, x, st));
+  AE_TRY(ae_head_forward(e, e->z, batch, logits, stream));
+  if (labels && loss_out) {
+    const double numel = (double)batch * 12288.0;
+    AE_TRY(softmax_ce(logits ? logits : e->logits, labels, batch, e->NC, 1.f, loss_out, nullptr, nullptr, e->sse, numel,
+                      alpha, st));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole-step CUDA graph
+// ---------------------------------------------------------------------------------------------
+struct ae_step_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels, int batch, float alpha, float* loss_out,
+                          float* flat_params, float* flat_grads, float* adam_m, float* adam_v, int64_t flat_len,
+                          const ae_adam_config_t* adam, int* step_dev, ae_dp_comm_t* comm, ae_stream_t stream,
+                          ae_step_graph_t** out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AE_CHECK(e && out && adam, "ae_step_graph_capture: null argument");
+  AE_CHECK(st != nullptr, "ae_step_graph_capture: needs a non-default stream");
+  AE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = ae_train_step(e, x, labels, batch, alpha, loss_out, stream);
+  float gscale = 1.f;
+  if (rc == 0 && comm) {
+    rc = ae_dp_allreduce(comm, flat_grads, flat_len, stream);
+    gscale = 1.f / (float)ae_dp_world(comm);
+  }
+  if (rc == 0)
+    rc = adam_step_flat(flat_params, flat_grads, adam_m, adam_v, flat_len, adam->lr, adam->beta1, adam->beta2, adam->eps,
+                        adam->weight_decay, gscale, step_dev, st);
+  for (int p = 0; rc == 0 && p < AE_NUM_PARTS; ++p) rc = ae_engine_pack_weights(e, p, stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) { set_error("ae_step_graph_capture: end capture failed: %s", cudaGetErrorString(ce)); return 1; }
+  ae_step_graph* g = new ae_step_graph();
+  g->graph = graph;
+  ce = cudaGraphInstantiate(&g->exec, graph, 0);
+  if (ce != cudaSuccess) {
+    set_error("ae_step_graph_capture: instantiate failed: %s", cudaGetErrorString(ce));
+    cudaGraphDestroy(graph);
+    delete g;
+    return 1;
+  }
+  *out = g;
+  return 0;
+}
+
+int ae_step_graph_launch(ae_step_graph_t* g, ae_stream_t stream) {
+  AE_CHECK(g && g->exec, "ae_step_graph_launch: null graph");
+  AE_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  return 0;
+}
+
+int ae_step_graph_num_kernels(const ae_step_graph_t* g) {
+  if (!g || !g->graph) return -1;
+  size_t n = 0;
+  if (cudaGraphGetNodes(g->graph, nullptr, &n) != cudaSuccess) return -1;
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n && cudaGraphGetNodes(g->graph, nodes.data(), &n) != cudaSuccess) return -1;
+  int k = 0;
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++k;
+  }
+  return k;
+}
+
+void ae_step_graph_destroy(ae_step_graph_t* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+"""Data-parallel plumbing: one process per GPU, torch.distributed for the rendezvous, one NCCL
+communicator owned by libae_b200 for the single flat-gradient allreduce per step."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check
+
+
+class Communicator:
+    def __init__(self, handle, rank, world):
+        self.handle, self.rank, self.world = handle, rank, world
+
+    def allreduce_(self, t: torch.Tensor):
+        check(_lib.load().ae_dp_allreduce(self.handle, C.c_void_p(t.data_ptr()), t.numel(),
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return t
+
+    def close(self):
+        if self.handle is not None:
+            _lib.load().ae_dp_destroy(self.handle)
+            self.handle = None
+
+
+def init_communicator() -> Communicator:
+    """Create the library's NCCL communicator; the unique id travels over the already-initialised
+    torch.distributed process group (any backend)."""
+    lib = _lib.load()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_uint8 * _lib.DP_UNIQUE_ID_BYTES)()
+    if rank == 0:
+        check(lib.ae_dp_get_unique_id(buf))
+    obj = [bytes(buf)]
+    dist.broadcast_object_list(obj, src=0)
+    raw = (C.c_uint8 * _lib.DP_UNIQUE_ID_BYTES).from_buffer_copy(obj[0])
+    h = C.c_void_p()
+    check(lib.ae_dp_init(raw, rank, world, C.byref(h)))
+    return Communicator(h, rank, world)
+
+
+def shard_bounds(total: int, rank: int, world: int):
+    """Contiguous batch shard [lo, hi) of `rank`: sizes differ by at most one, all shards non-empty when total >= world."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def broadcast_parameters(model, src: int = 0):
+    """Make every rank start from rank `src`'s parameters and buffers (torch.distributed plumbing)."""
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src=src)

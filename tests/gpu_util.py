@@ -1,0 +1,94 @@
+"""Helpers for the -m gpu parity tests: call the C ABI (include/ae_b200.h) with torch tensors."""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+import ae_b200
+from ae_b200 import _lib
+
+BACKENDS = [b for b in os.environ.get("AE_TEST_BACKENDS", "simt,tc").split(",") if b]
+PRECISIONS = ["fp32", "bf16"]
+PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+BACK = {"tc": _lib.BACKEND_TC, "simt": _lib.BACKEND_SIMT}
+# tolerances stated by BASELINE.json's north_star: fp32 rel <= 1e-4, bf16 rel <= 1e-2 (rel = max|a-b| / max|b|)
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def lib():
+    return _lib.load()
+
+
+def p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def operand(src, src2=None, bnc=None, scalar=0.0, mode=_lib.OP_RAW):
+    return _lib.Operand(p(src), p(src2), p(bnc), float(scalar), int(mode))
+
+
+def epilogue(mode=_lib.EPI_STORE, bias=None, y=None, bnc=None, stats=None):
+    return _lib.Epilogue(int(mode), p(bias), p(y), p(bnc), p(stats))
+
+
+def make_bnc(C_, rs, device):
+    """Random but sane coefficient block [8][C]."""
+    b = torch.zeros(8, C_)
+    b[0] = torch.from_numpy(rs.uniform(0.5, 1.5, C_).astype(np.float32))       # scale
+    b[1] = torch.from_numpy(rs.uniform(-0.3, 0.3, C_).astype(np.float32))      # shift
+    b[2] = torch.from_numpy(rs.uniform(-0.3, 0.3, C_).astype(np.float32))      # mean
+    b[3] = torch.from_numpy(rs.uniform(0.5, 2.0, C_).astype(np.float32))       # rstd
+    b[4] = torch.from_numpy(rs.uniform(0.5, 1.5, C_).astype(np.float32))       # A
+    b[5] = torch.from_numpy(rs.uniform(-0.2, 0.2, C_).astype(np.float32))      # B
+    b[6] = torch.from_numpy(rs.uniform(-0.1, 0.1, C_).astype(np.float32))      # C
+    return b.to(device)
+
+
+def pack_conv(w, cs, cb, prec, backend):
+    n = lib().ae_packed_weight_bytes(cs, cb, PREC[prec], BACK[backend])
+    fwd = torch.zeros(n + 1024, dtype=torch.uint8, device=w.device)
+    dg = torch.zeros(n + 1024, dtype=torch.uint8, device=w.device)
+    # 1024-byte aligned views (TMA bulk copies want aligned sources)
+    def al(t):
+        off = (-t.data_ptr()) % 1024
+        return t[off:off + n]
+    f, d = al(fwd), al(dg)
+    _lib.check(lib().ae_pack_conv_weight(p(w), cs, cb, p(f), p(d), PREC[prec], BACK[backend], stream()))
+    return f, d
+
+
+def load_ae(model, seed, latent=64):
+    from oracle import seeded
+    st = seeded.seeded_state(seeded.ae_state_shapes(latent, 10), seed)
+    model.load_state_dict(st)
+    return st
+
+
+def load_mlp(model, seed):
+    from oracle import seeded
+    st = seeded.seeded_state(seeded.mlp_state_shapes(64, 10), seed)
+    model.load_state_dict(st)
+    return st
