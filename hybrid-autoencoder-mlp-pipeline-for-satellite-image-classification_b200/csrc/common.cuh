@@ -128,13 +128,16 @@ __device__ __forceinline__ float4 load_operand4(const Operand& op, size_t off, i
   }
   // AE_OP_BNBWD
   const float4 y = __ldg(reinterpret_cast<const float4*>(op.src2 + off));
+  // dy = A*dz + B*(y - mean) + C.  (y - mean) is formed first: folding B*mean into C would turn the per-channel
+  // rounding of C into an offset that coherent sums (next layer's statistics, weight gradients) amplify.
   const float4 a = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_A * op.C + c));
   const float4 b = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_B * op.C + c));
   const float4 k = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_C * op.C + c));
-  v.x = fmaf(a.x, v.x, fmaf(b.x, y.x, k.x));
-  v.y = fmaf(a.y, v.y, fmaf(b.y, y.y, k.y));
-  v.z = fmaf(a.z, v.z, fmaf(b.z, y.z, k.z));
-  v.w = fmaf(a.w, v.w, fmaf(b.w, y.w, k.w));
+  const float4 m = __ldg(reinterpret_cast<const float4*>(op.bnc + AE_BNC_MEAN * op.C + c));
+  v.x = fmaf(a.x, v.x, fmaf(b.x, y.x - m.x, k.x));
+  v.y = fmaf(a.y, v.y, fmaf(b.y, y.y - m.y, k.y));
+  v.z = fmaf(a.z, v.z, fmaf(b.z, y.z - m.z, k.z));
+  v.w = fmaf(a.w, v.w, fmaf(b.w, y.w - m.w, k.w));
   return v;
 }
 

@@ -46,16 +46,16 @@ int bn_finalize(const double* stats, int64_t count, const float* gamma, const fl
   return 0;
 }
 
-// dy = A*dz + B*y + C with  A = gamma*rstd,  B = -A*rstd*S2/M,  C = -A*S1/M - B*mean
+// dy = A*dz + B*(y - mean) + C with  A = gamma*rstd,  B = -A*rstd*S2/M,  C = -A*S1/M
 __global__ void k_bn_bwd_reduce(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                                 float* __restrict__ bnc, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double s1 = stats[c], s2 = stats[C + c];
-  const double rstd = (double)bnc[AE_BNC_RSTD * C + c], mean = (double)bnc[AE_BNC_MEAN * C + c];
+  const double rstd = (double)bnc[AE_BNC_RSTD * C + c];
   const double a = (double)gamma[c] * rstd;
   const double b = -a * rstd * s2 / count;
-  const double k = -a * s1 / count - b * mean;
+  const double k = -a * s1 / count;
   bnc[AE_BNC_A * C + c] = (float)a;
   bnc[AE_BNC_B * C + c] = (float)b;
   bnc[AE_BNC_C * C + c] = (float)k;

@@ -349,8 +349,8 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
       cluster_sum(cl, part, 4, 2 * H2, tot);
       for (int k = tid; k < H2; k += NT) {
         const double S1 = tot[k], S2 = tot[H2 + k];
-        const double rstd = c2[3 * H1 + k], mean = c2[2 * H1 + k];
-        const double A = (double)g2[k] * rstd, Bc = -A * rstd * S2 / B, Cc = -A * S1 / B - Bc * mean;
+        const double rstd = c2[3 * H1 + k];
+        const double A = (double)g2[k] * rstd, Bc = -A * rstd * S2 / B, Cc = -A * S1 / B;
         c2[4 * H1 + k] = (float)A; c2[5 * H1 + k] = (float)Bc; c2[6 * H1 + k] = (float)Cc;
         if (rank == 0) { gp[a.off[6] + k] = (float)S2; gp[a.off[7] + k] = (float)S1; gp[a.off[5] + k] = 0.f; }
       }
@@ -384,7 +384,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
           float v = 0.f;
           if (r < nv) {
             const size_t g = (size_t)(c0 + r) * H2 + k;
-            v = fmaf(c2[4 * H1 + k], a.d2[g], fmaf(c2[5 * H1 + k], a.h2[g], c2[6 * H1 + k]));
+            v = fmaf(c2[4 * H1 + k], a.d2[g], fmaf(c2[5 * H1 + k], a.h2[g] - c2[2 * H1 + k], c2[6 * H1 + k]));
           }
           stg1[k * CHUNK + r] = v;
         }
@@ -439,8 +439,8 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
       cluster_sum(cl, part, 2, 2 * H1, tot);
       for (int k = tid; k < H1; k += NT) {
         const double S1 = tot[k], S2 = tot[H1 + k];
-        const double rstd = c1[3 * H1 + k], mean = c1[2 * H1 + k];
-        const double A = (double)g1[k] * rstd, Bc = -A * rstd * S2 / B, Cc = -A * S1 / B - Bc * mean;
+        const double rstd = c1[3 * H1 + k];
+        const double A = (double)g1[k] * rstd, Bc = -A * rstd * S2 / B, Cc = -A * S1 / B;
         c1[4 * H1 + k] = (float)A; c1[5 * H1 + k] = (float)Bc; c1[6 * H1 + k] = (float)Cc;
         if (rank == 0) { gp[a.off[2] + k] = (float)S2; gp[a.off[3] + k] = (float)S1; gp[a.off[1] + k] = 0.f; }
       }
@@ -469,7 +469,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
           float v = 0.f;
           if (r < nv) {
             const size_t g = (size_t)(c0 + r) * H1 + k;
-            v = fmaf(c1[4 * H1 + k], a.d1[g], fmaf(c1[5 * H1 + k], a.h1[g], c1[6 * H1 + k]));
+            v = fmaf(c1[4 * H1 + k], a.d1[g], fmaf(c1[5 * H1 + k], a.h1[g] - c1[2 * H1 + k], c1[6 * H1 + k]));
           }
           stg0[k * CHUNK + r] = v;
         }

@@ -62,14 +62,14 @@ class _Flat:
                 self.data[off:off + n].copy_(p.detach().reshape(-1).to(device=device, dtype=torch.float32))
                 p.data = self.data[off:off + n].view(p.shape)
                 p._ae_flat = (self, off)
-        self.versions = None
+        self.generation = 0      # bumped by code that changes the parameters through raw pointers (fused Adam)
 
     def aliased(self) -> bool:
         base = self.data.data_ptr()
         return all(p.data_ptr() == base + 4 * off for p, off in zip(self.params, self.offsets))
 
     def version_sum(self) -> int:
-        return sum(p._version for p in self.params)
+        return sum(p._version for p in self.params) + (self.generation << 32)
 
     def grad_views(self, src: torch.Tensor):
         return [src[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.offsets)]

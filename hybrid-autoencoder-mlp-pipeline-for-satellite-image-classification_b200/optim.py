@@ -84,6 +84,7 @@ class Adam(torch.optim.Optimizer):
                                             float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                             float(group["weight_decay"]), float(self.grad_scale), ptr(st["step"]),
                                             stream_ptr()))
+                flat.generation += 1
                 for q, o, val in keep:
                     flat.data[o:o + q.numel()].copy_(val.reshape(-1))
                     st["m"][o:o + q.numel()].zero_()

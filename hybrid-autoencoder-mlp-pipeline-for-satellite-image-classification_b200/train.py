@@ -53,11 +53,17 @@ class TrainStep:
 
     def run(self):
         check(_lib.load().ae_step_graph_launch(self.handle, C.c_void_p(self.stream.cuda_stream)))
-        self._eng.mark_packed()
+        self._eng.flat.generation += 1
+        self._eng.mark_packed()      # the graph re-packs the weights itself
 
     def __call__(self, imgs, labels):
+        """One step with torch stream semantics: inputs produced on the current stream are waited for, and the
+        returned loss tensor [loss, mse, ce] is safe to read from the current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
         self.load(imgs, labels)
         self.run()
+        cur.wait_stream(self.stream)
         return self.loss[:3]
 
     def __del__(self):

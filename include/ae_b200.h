@@ -48,7 +48,7 @@ enum {
 enum {
   AE_OP_RAW = 0,        /* value = src */
   AE_OP_BNRELU = 1,     /* value = relu(src * scale[c] + shift[c])                (BatchNorm + ReLU forward) */
-  AE_OP_BNBWD = 2,      /* value = A[c] * src + B[c] * src2 + C[c]                (BatchNorm backward apply) */
+  AE_OP_BNBWD = 2,      /* value = A[c] * src + B[c] * (src2 - mean[c]) + C[c]    (BatchNorm backward apply) */
   AE_OP_SIGMOID_BWD = 3 /* value = up * s * (1 - s), s = src2 (sigmoid output): up = src, or scalar * (s - src) when fused MSE */
 };
 
@@ -146,7 +146,7 @@ size_t ae_thin_wgrad_workspace_bytes(int batch);
  *   training update running_mean / running_var (unbiased) in place.  training == 0: scale/shift
  *   from the running statistics (stats may be NULL).
  * ae_bn_bwd_reduce: from fp64 sums (sum dz, sum dz*xhat) write dgamma, dbeta and the backward
- *   apply coefficients A, B, C into `bnc` (dy = A*dz + B*y + C).
+ *   apply coefficients A, B, C into `bnc` (dy = A*dz + B*(y - mean) + C).
  * ---------------------------------------------------------------------------------------- */
 int ae_bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, float* bnc, int channels, int training,

@@ -38,6 +38,12 @@ def rel(a, b):
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
 
 
+def rel_l2(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
 def nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 

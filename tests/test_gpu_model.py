@@ -91,13 +91,20 @@ def test_ae_dropin_training_loop_golden(tag, backend, prec):
 @pytest.mark.parametrize("backend,prec", CONFIGS)
 @pytest.mark.parametrize("batch", [1, 33, 256])
 def test_ae_fused_train_step_vs_oracle(batch, backend, prec):
-    """ae_train_step (forward + alpha*MSE + CE + backward in the library) against the oracle's autograd."""
+    """ae_train_step (forward + alpha*MSE + CE + backward in the library) against the oracle's autograd.
+
+    Gradients are compared with the oracle evaluated in fp64, in relative L2 norm.  The gradient is a
+    discontinuous function of the activations: a pre-activation within one ulp of zero takes the other ReLU branch
+    in another arithmetic, which moves individual weight-gradient entries by ~1/sqrt(pixels) (measured: the fp32
+    CPU reference itself differs from fp64 by up to 4e-3 of max|g| on single entries at batch 256, see DESIGN.md
+    'gradient conditioning').  The max-norm is therefore only bounded loosely; losses use the fp32 oracle."""
     seed, alpha = 11, 35.0
     st = seeded.seeded_state(seeded.ae_state_shapes(64, 10), seed)
     x, y = seeded.seeded_images(batch, seed), seeded.seeded_labels(batch, seed)
     ref_state = {k: v.clone() for k, v in st.items()}
-    opt = {}
-    loss, lrec, lcls, grads, (x_hat, logits, z) = tp.ae_train_step(ref_state, opt, x, y, alpha, 5e-3)
+    loss, lrec, lcls, grads32, (x_hat, logits, z) = tp.ae_train_step(ref_state, {}, x, y, alpha, 5e-3)
+    st64 = {k: (v.double() if v.dtype == torch.float32 else v.clone()) for k, v in st.items()}
+    _, _, _, grads, _ = tp.ae_train_step(st64, {}, x.double(), y, alpha, 5e-3)
     model = _model(64, backend, prec)
     model.load_state_dict(st)
     model = model.to(gu.dev()).train()
@@ -105,27 +112,34 @@ def test_ae_fused_train_step_vs_oracle(batch, backend, prec):
     torch.cuda.synchronize()
     tol = gu.TOL[prec]
     got = out.cpu()
-    assert abs(float(got[0]) - float(loss)) <= tol * 10 * abs(float(loss))
-    assert abs(float(got[1]) - float(lrec)) <= tol * 10 * abs(float(lrec))
-    assert abs(float(got[2]) - float(lcls)) <= tol * 10 * abs(float(lcls))
+    assert abs(float(got[0]) - float(loss)) <= tol * abs(float(loss))
+    assert abs(float(got[1]) - float(lrec)) <= tol * abs(float(lrec))
+    assert abs(float(got[2]) - float(lcls)) <= tol * abs(float(lcls))
     worst = ("", 0.0)
+    worst32 = 0.0
     for k, p in model.named_parameters():
         if k in gu_gold.NOISE_BIAS:
-            assert float(p.grad.abs().max()) <= 1e-5 * (1.0 + float(grads[k].abs().max()))
+            assert float(p.grad.abs().max()) == 0.0     # mathematically zero; the library writes exact zeros
             continue
-        r = gu.rel(p.grad, grads[k])
+        r = gu.rel_l2(p.grad, grads[k])
+        worst32 = max(worst32, gu.rel_l2(grads32[k], grads[k]))
         if r > worst[1]:
             worst = (k, r)
-    assert worst[1] <= tol * 10, worst
+        assert gu.rel(p.grad, grads[k]) <= max(2e-2, tol * 10), k
+    print(f"batch {batch}: worst gradient rel-L2 vs fp64 oracle: ours {worst[1]:.2e} ({worst[0]}), fp32 CPU reference {worst32:.2e}")
+    assert worst[1] <= tol * 10, (worst, worst32)
     if batch > 1:
         for k, v in model.state_dict().items():
             if k.endswith("running_var") or k.endswith("running_mean"):
-                assert gu.rel(v, ref_state[k]) <= tol * 10, k
+                assert gu.rel(v, ref_state[k]) <= tol, k
 
 
 @pytest.mark.parametrize("backend,prec", CONFIGS)
 def test_train_step_graph_matches_oracle_over_steps(backend, prec):
-    """Whole-step CUDA graph (train step + Adam + re-pack) for 4 steps against the oracle loop."""
+    """Whole-step CUDA graph (train step + Adam + re-pack) against the oracle loop.  After ONE step the parameters
+    must agree tightly.  Later steps are compared through the loss only: with lr = 5e-3 the first Adam steps move
+    every weight by +-lr, the loss jumps from 5.9 to 9.5, and the fp32 and fp64 CPU oracles themselves drift apart
+    (25 % of conv1's weights differ by > 0.1 lr after 4 steps; measured, DESIGN.md 'gradient conditioning')."""
     seed, alpha, lr, batch, steps = 21, 35.0, 5e-3, 16, 4
     st = seeded.seeded_state(seeded.ae_state_shapes(64, 10), seed)
     ref_state = {k: v.clone() for k, v in st.items()}
@@ -136,18 +150,22 @@ def test_train_step_graph_matches_oracle_over_steps(backend, prec):
     model.engine().prepare(gu.dev(), batch)
     optimizer = ae_b200.Adam(model.parameters(), lr=lr)
     stepper = ae_b200.TrainStep(model, optimizer, alpha, batch)
+    assert stepper.num_kernels > 0
     tol = gu.TOL[prec]
     for s in range(steps):
         x, y = seeded.seeded_images(batch, seed + s), seeded.seeded_labels(batch, seed + s)
         loss, *_ = tp.ae_train_step(ref_state, opt, x, y, alpha, lr)
         got = stepper(x.pin_memory(), y.pin_memory())
-        stepper.stream.synchronize()
-        assert abs(float(got[0]) - float(loss)) <= tol * 50 * abs(float(loss)), (s, float(got[0]), float(loss))
-    torch.cuda.synchronize()
-    for k, p in model.named_parameters():
-        if k in gu_gold.NOISE_BIAS:
-            continue
-        assert float((p.detach().cpu() - ref_state[k]).abs().max()) <= max(tol * 50, 2e-3) * float(ref_state[k].abs().max()) + lr * 0.05, k
+        assert abs(float(got[0]) - float(loss)) <= max(tol * 50, 2e-3) * abs(float(loss)), (s, float(got[0]), float(loss))
+        if s == 0:
+            for k, p in model.named_parameters():
+                if k in gu_gold.NOISE_BIAS:
+                    continue
+                d = (p.detach().cpu() - ref_state[k]).abs()
+                if prec == "fp32":
+                    assert float(d.max()) <= 1e-3 * lr, (k, float(d.max()))
+                else:
+                    assert float((d > 0.1 * lr).float().mean()) <= 0.02, k
 
 
 @pytest.mark.parametrize("backend,prec", CONFIGS)
@@ -202,40 +220,56 @@ def test_encode_predict_golden_and_argmax(backend, prec):
 
 
 def test_argmax_identical_on_structured_data_after_training():
-    """Class-structured data + a short training run, then argmax of clf(enc(x)) must equal the oracle's
-    (SURVEY hard-part: argmax parity is meaningless at random init)."""
+    """Class-structured data + a short training run on the GPU, then clf(enc(x)).argmax(1) must equal the oracle's on
+    the SAME trained weights (SURVEY hard-part: argmax parity is meaningless at random init)."""
     seed, alpha, lr, batch = 8, 35.0, 2e-3, 64
     st = seeded.seeded_state(seeded.ae_state_shapes(64, 10), seed)
-    mst = seeded.seeded_state(seeded.mlp_state_shapes(64, 10), seed + 1)
-    ref_state = {k: v.clone() for k, v in st.items()}
-    opt = {}
-    model = ae_b200.SupervisedAutoencoder(64, 10)
+    model = ae_b200.SupervisedAutoencoder(64, 10, backend=gu.BACKENDS[-1])
     model.load_state_dict(st)
     model = model.to(gu.dev()).train()
     model.engine().prepare(gu.dev(), batch)
     optimizer = ae_b200.Adam(model.parameters(), lr=lr)
     stepper = ae_b200.TrainStep(model, optimizer, alpha, batch)
-    for s in range(30):
+    first = None
+    for s in range(40):
         y = seeded.seeded_labels(batch, 2000 + s)
         x = seeded.structured_images(y, 2000 + s)
-        tp.ae_train_step(ref_state, opt, x, y, alpha, lr)
-        stepper(x, y)
+        out = stepper(x, y)
+        if first is None:
+            first = out.clone()
     torch.cuda.synchronize()
+    assert float(out[2]) < float(first[2])               # cross-entropy went down: the classes are learnable
+    # a classifier on the latents: train the MLP for a few steps on the GPU too
+    clf = ae_b200.MLP(64, 10).to(gu.dev())
+    gu.load_mlp(clf, seed + 1)
+    clf = clf.to(gu.dev()).train()
+    model.eval()
+    clf(torch.zeros(4, 64, device=gu.dev()))
+    gu.load_mlp(clf, seed + 1)
+    copt = ae_b200.Adam(clf.parameters(), lr=1e-2, weight_decay=1e-4)
+    for s in range(60):
+        y = seeded.seeded_labels(256, 2500 + s)
+        x = seeded.structured_images(y, 2500 + s).to(gu.dev())
+        with torch.no_grad():
+            zt = model.enc(x)
+        copt.zero_grad()
+        clf.fused_step_grads(zt, y.to(gu.dev()))
+        copt.step()
     y = seeded.seeded_labels(512, 3000)
     x = seeded.structured_images(y, 3000)
-    zr, lr_ = tp.encode_predict(ref_state, mst, x)
-    clf = ae_b200.MLP(64, 10)
-    clf.load_state_dict(mst)
-    clf = clf.to(gu.dev())
-    model.eval()
+    ref_ae = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ref_clf = {k: v.detach().cpu().clone() for k, v in clf.state_dict().items()}
+    zr, lr_ = tp.encode_predict(ref_ae, ref_clf, x)
     z, logits, am = ae_b200.encode_predict(model.enc, clf, x.to(gu.dev()))
+    assert gu.rel(z, zr) <= 1e-4 and gu.rel(logits, lr_) <= 1e-4
     ref_am = lr_.argmax(1)
+    assert len(set(ref_am.tolist())) >= 5, "degenerate predictions: the test would not discriminate"
+    acc = float((ref_am == y).float().mean())
+    assert acc > 0.5, acc
     top2 = lr_.topk(2, dim=1).values
-    margin = (top2[:, 0] - top2[:, 1])
-    safe = margin > 1e-3 * float(lr_.abs().max())      # exclude numerical ties
-    assert int(safe.sum()) > 400
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-4 * float(lr_.abs().max())      # exclude numerical ties
+    assert int(safe.sum()) >= 500
     assert torch.equal(am.cpu()[safe], ref_am[safe])
-    assert len(set(ref_am.tolist())) > 1
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -289,15 +323,20 @@ def test_mlp_fused_step_vs_oracle(batch):
     y = seeded.seeded_labels(batch, seed)
     keep = torch.from_numpy((rs.random_sample((batch, 128)) >= 0.3).astype(np.float32))
     ref_state = {k: v.clone() for k, v in st.items()}
-    loss, grads, logits = tp.mlp_train_step(ref_state, {}, x, y, 1e-3, 1e-4, keep)
-    clf = ae_b200.MLP(64, 10)
-    clf.load_state_dict(st)
-    clf = clf.to(gu.dev()).train()
-    clf.set_dropout_keep_mask(keep)
-    gl, gc, glogits = clf.fused_step_grads(x.to(gu.dev()), y.to(gu.dev()))
-    torch.cuda.synchronize()
+    if batch > 1:
+        loss, grads, logits = tp.mlp_train_step(ref_state, {}, x, y, 1e-3, 1e-4, keep)
+        clf = ae_b200.MLP(64, 10)
+        clf.load_state_dict(st)
+        clf = clf.to(gu.dev()).train()
+        clf.set_dropout_keep_mask(keep)
+        gl, gc, glogits = clf.fused_step_grads(x.to(gu.dev()), y.to(gu.dev()))
+        torch.cuda.synchronize()
     if batch == 1:
-        return  # BatchNorm over one sample: torch raises in training mode; only check that the kernel runs
+        # BatchNorm over one sample: torch raises in training mode; only check that the kernel runs and is finite
+        clf = ae_b200.MLP(64, 10); clf.load_state_dict(st); clf = clf.to(gu.dev()).train()
+        gl, gc, glogits = clf.fused_step_grads(x.to(gu.dev()), y.to(gu.dev()))
+        assert torch.isfinite(gl).all() and torch.isfinite(glogits).all()
+        return
     assert abs(float(gl) - float(loss)) <= 1e-5 * max(1.0, abs(float(loss)))
     assert gu.rel(glogits, logits) <= 1e-4
     assert int(gc) == int((logits.argmax(1) == y).sum())
@@ -348,7 +387,7 @@ def test_no_cpu_fallback_and_errors():
 
 def test_frozen_encoder_and_feature_extraction():
     """NB:3434-3441: freeze best_ae.enc, extract latents over a loader of ragged batches."""
-    ae = ae_b200.SupervisedAutoencoder(64).to(gu.dev())
+    ae = ae_b200.SupervisedAutoencoder(64, backend=gu.BACKENDS[-1]).to(gu.dev())
     st = gu.load_ae(ae, 12)
     for p in ae.enc.parameters():
         p.requires_grad = False

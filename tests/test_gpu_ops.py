@@ -28,7 +28,7 @@ def _apply_operand_cpu(mode, src, src2, bnc):
         return src
     if mode == _lib.OP_BNRELU:
         return torch.relu(src * v(0) + v(1))
-    return v(4) * src + v(5) * src2 + v(6)
+    return v(4) * src + v(5) * (src2 - v(2)) + v(6)
 
 
 @pytest.mark.parametrize("backend", gu.BACKENDS)
@@ -94,7 +94,8 @@ def test_conv_dgrad_is_transposed_conv(shape, mode, prec, backend):
     wd = w.to(d)
     _, pd = gu.pack_conv(wd, cs, cb, prec, backend)
     g = _geom(b, hs, cb, cs)
-    op = gu.operand(gu.nhwc(small).to(d), gu.nhwc(small2).to(d), bnc.to(d), 0.0, mode)
+    sd, sd2, bncd = gu.nhwc(small).to(d), gu.nhwc(small2).to(d), bnc.to(d)   # keep alive: operand holds raw pointers
+    op = gu.operand(sd, sd2, bncd, 0.0, mode)
     out = torch.empty(b, 2 * hs, 2 * hs, cb, device=d)
     stats = torch.zeros(2 * cb, dtype=torch.float64, device=d)
     biasd = bias.to(d)
@@ -139,8 +140,9 @@ def test_conv_wgrad(shape, prec, backend):
     nbytes = gu.lib().ae_conv2d_s2_wgrad_workspace_bytes(C.byref(g), gu.PREC[prec], gu.BACK[backend])
     part = torch.empty(nbytes + 16, dtype=torch.uint8, device=d)
     dw = torch.full((cs, cb, 3, 3), float("nan"), device=d)
-    opb = gu.operand(gu.nhwc(big).to(d), None, bnc_b.to(d), 0.0, _lib.OP_BNRELU)
-    ops = gu.operand(gu.nhwc(dz).to(d), gu.nhwc(y).to(d), bnc_s.to(d), 0.0, _lib.OP_BNBWD)
+    bigd, bncbd, dzd, yd, bncsd = gu.nhwc(big).to(d), bnc_b.to(d), gu.nhwc(dz).to(d), gu.nhwc(y).to(d), bnc_s.to(d)
+    opb = gu.operand(bigd, None, bncbd, 0.0, _lib.OP_BNRELU)
+    ops = gu.operand(dzd, yd, bncsd, 0.0, _lib.OP_BNBWD)
     _lib.check(gu.lib().ae_conv2d_s2_wgrad(C.byref(g), C.byref(opb), C.byref(ops), gu.p(dw), gu.p(part), nbytes,
                                           gu.PREC[prec], gu.BACK[backend], gu.stream()))
     torch.cuda.synchronize()
@@ -241,7 +243,7 @@ def test_bn_finalize_and_backward_coefficients():
     torch.cuda.synchronize()
     assert gu.rel(dg, gr.grad) <= 1e-5 and gu.rel(db, br.grad) <= 1e-5
     b = bnc.cpu()
-    dy = b[4].view(1, -1, 1, 1) * dz + b[5].view(1, -1, 1, 1) * y + b[6].view(1, -1, 1, 1)
+    dy = b[4].view(1, -1, 1, 1) * dz + b[5].view(1, -1, 1, 1) * (y - b[2].view(1, -1, 1, 1)) + b[6].view(1, -1, 1, 1)
     assert gu.rel(dy, yr.grad) <= 2e-5
     # eval mode: coefficients from the running statistics
     bnc2 = torch.zeros(8, Cn, device=d)
