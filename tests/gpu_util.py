@@ -14,6 +14,11 @@ PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
 BACK = {"tc": _lib.BACKEND_TC, "simt": _lib.BACKEND_SIMT}
 # tolerances stated by BASELINE.json's north_star: fp32 rel <= 1e-4, bf16 rel <= 1e-2 (rel = max|a-b| / max|b|)
 TOL = {"fp32": 1e-4, "bf16": 1e-2}
+# Gradients (no tolerance is stated for them; measured, see DESIGN.md 'gradient conditioning').  Relative L2 against
+# the fp64 oracle.  BatchNorm's backward removes the batch-mean and the xhat-correlated part of the incoming gradient,
+# which amplifies the relative error of whatever arithmetic produced it by |dz|/|dy| (10-100x in this network):
+# fp32 CUDA cores (1e-7) -> ~1e-5, 2-term bf16 split on tcgen05 (1e-5) -> ~3e-3, plain bf16 (4e-3) -> ~0.2.
+GRAD_TOL = {("simt", "fp32"): 1e-3, ("tc", "fp32"): 1e-2, ("tc", "bf16"): 0.35}
 
 
 def dev():
