@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libae_b200.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
 BACKEND_TC, BACKEND_SIMT = 0, 1
-OP_RAW, OP_BNRELU, OP_BNBWD, OP_SIGMOID_BWD = 0, 1, 2, 3
+OP_RAW, OP_BNRELU, OP_BNBWD, OP_SIGMOID_BWD, OP_SPLIT_BF16 = 0, 1, 2, 3, 4
 EPI_STORE, EPI_BIAS_STATS, EPI_RELUBWD_STATS = 0, 1, 2
 PART_ENC, PART_DEC, PART_HEAD = 0, 1, 2
 BNC_ROWS = 8
@@ -49,6 +49,8 @@ _SIGS = {
     "ae_device_supported": (c_int, [c_int]),
     "ae_packed_weight_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "ae_pack_conv_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "ae_split_operand_bytes": (c_size_t, [c_int64, c_int]),
+    "ae_split_operand": (c_int, [P(Operand), c_int, c_int64, c_void_p, c_int, c_void_p]),
     "ae_conv2d_s2_fwd": (c_int, [P(ConvGeom), P(Operand), c_void_p, P(Epilogue), c_void_p, c_int, c_int, c_void_p]),
     "ae_conv2d_s2_dgrad": (c_int, [P(ConvGeom), P(Operand), c_void_p, P(Epilogue), c_void_p, c_int, c_int, c_void_p]),
     "ae_conv2d_s2_wgrad_workspace_bytes": (c_size_t, [P(ConvGeom), c_int, c_int]),

@@ -64,14 +64,21 @@ int ae_device_supported(int ordinal) {
 
 size_t ae_packed_weight_bytes(int cs, int cb, int precision, int backend) {
   if (backend == AE_BACKEND_SIMT) return (size_t)9 * cs * cb * sizeof(float);
-  return tc_packed_bytes(cs, cb, nsplit_of(precision));
+  return tma_packed_bytes(cs, cb, nsplit_of(precision));
+}
+
+size_t ae_split_operand_bytes(int64_t count, int precision) { return (size_t)count * 2 * nsplit_of(precision); }
+
+int ae_split_operand(const ae_operand_t* op, int channels, int64_t count, void* planes, int precision, ae_stream_t stream) {
+  AE_CHECK(op && op->src && planes && channels >= 8 && count >= 8, "ae_split_operand: bad argument");
+  return tma_split_operand(make_operand(op, channels), count, planes, nsplit_of(precision), (cudaStream_t)stream);
 }
 
 int ae_pack_conv_weight(const float* w, int cs, int cb, void* packed_fwd, void* packed_dgrad, int precision, int backend,
                         ae_stream_t stream) {
   AE_CHECK(w != nullptr, "ae_pack_conv_weight: null weight");
   if (backend == AE_BACKEND_SIMT) return pack_conv_simt(w, cs, cb, (float*)packed_fwd, (float*)packed_dgrad, (cudaStream_t)stream);
-  return tc_pack_conv(w, cs, cb, nsplit_of(precision), packed_fwd, packed_dgrad, (cudaStream_t)stream);
+  return tma_pack_conv(w, cs, cb, nsplit_of(precision), packed_fwd, packed_dgrad, (cudaStream_t)stream);
 }
 
 int ae_conv2d_s2_fwd(const ae_conv_geom_t* g, const ae_operand_t* big, const void* packed_fwd, const ae_epilogue_t* epi,
@@ -83,8 +90,8 @@ int ae_conv2d_s2_fwd(const ae_conv_geom_t* g, const ae_operand_t* big, const voi
   r.A = make_operand(big, r.g.Cb); r.Bp = (const float*)packed_fwd; r.epi = make_epilogue(epi, r.g.Cs);
   r.out = out_small; r.splitK = 1;
   if (backend == AE_BACKEND_SIMT) return simt_rowgemm(r, (cudaStream_t)stream);
-  AE_CHECK(tc_rowgemm_supported(r), "ae_conv2d_s2_fwd: shape not supported by the tcgen05 path");
-  return tc_rowgemm(r, packed_fwd, nsplit_of(precision), (cudaStream_t)stream);
+  AE_CHECK(tma_rowgemm_supported(r), "ae_conv2d_s2_fwd: shape not supported by the tcgen05 path");
+  return tma_rowgemm(r, packed_fwd, nsplit_of(precision), (cudaStream_t)stream);
 }
 
 int ae_conv2d_s2_dgrad(const ae_conv_geom_t* g, const ae_operand_t* small, const void* packed_dgrad,
@@ -96,13 +103,18 @@ int ae_conv2d_s2_dgrad(const ae_conv_geom_t* g, const ae_operand_t* small, const
   r.A = make_operand(small, r.g.Cs); r.Bp = (const float*)packed_dgrad; r.epi = make_epilogue(epi, r.g.Cb);
   r.out = out_big; r.splitK = 1;
   if (backend == AE_BACKEND_SIMT) return simt_rowgemm(r, (cudaStream_t)stream);
-  AE_CHECK(tc_rowgemm_supported(r), "ae_conv2d_s2_dgrad: shape not supported by the tcgen05 path");
-  return tc_rowgemm(r, packed_dgrad, nsplit_of(precision), (cudaStream_t)stream);
+  AE_CHECK(tma_rowgemm_supported(r), "ae_conv2d_s2_dgrad: shape not supported by the tcgen05 path");
+  return tma_rowgemm(r, packed_dgrad, nsplit_of(precision), (cudaStream_t)stream);
 }
 
 size_t ae_conv2d_s2_wgrad_workspace_bytes(const ae_conv_geom_t* g, int precision, int backend) {
-  (void)precision; (void)backend;
+  (void)precision;
   if (!g) return 0;
+  if (backend == AE_BACKEND_TC) {
+    Geom gg;
+    if (make_geom(g, &gg) != 0) return 0;
+    return tma_wgrad_partial_bytes(gg);
+  }
   const int M = g->batch * g->hs * g->ws, I = 9 * g->cb, J = g->cs;
   return (size_t)colgemm_default_split(M, I, J) * I * J * sizeof(float);
 }
@@ -112,6 +124,11 @@ int ae_conv2d_s2_wgrad(const ae_conv_geom_t* g, const ae_operand_t* big, const a
   ColGemm c{};
   AE_TRY(make_geom(g, &c.g));
   AE_CHECK(big && small && dw, "ae_conv2d_s2_wgrad: null argument");
+  if (backend == AE_BACKEND_TC) {
+    AE_CHECK(big->mode == AE_OP_SPLIT_BF16 && small->mode == AE_OP_SPLIT_BF16,
+             "ae_conv2d_s2_wgrad: the tcgen05 path takes split-bf16 operands (ae_split_operand)");
+    return tma_wgrad(c.g, big->src, small->src, dw, (float*)partials, partials_bytes, nsplit_of(precision), (cudaStream_t)stream);
+  }
   c.gather = 1; c.M = c.g.B * c.g.Hs * c.g.Ws; c.I = 9 * c.g.Cb; c.J = c.g.Cs;
   c.A = make_operand(big, c.g.Cb); c.B = make_operand(small, c.g.Cs);
   c.out = dw; c.permC = c.g.Cb; c.permHW = 9; c.transposed = 1;
@@ -119,8 +136,7 @@ int ae_conv2d_s2_wgrad(const ae_conv_geom_t* g, const ae_operand_t* big, const a
   c.partial = (float*)partials;
   AE_CHECK(c.splitK == 1 || (partials && partials_bytes >= (size_t)c.splitK * c.I * c.J * 4),
            "ae_conv2d_s2_wgrad: partial buffer too small (%zu bytes)", partials_bytes);
-  if (backend == AE_BACKEND_SIMT) return simt_colgemm(c, (cudaStream_t)stream);
-  return tc_wgrad(c, nsplit_of(precision), (cudaStream_t)stream);
+  return simt_colgemm(c, (cudaStream_t)stream);
 }
 
 int ae_thin_gather_fwd(const ae_operand_t* thin, const float* w, const ae_epilogue_t* epi, float* out_wide, int batch,

@@ -78,6 +78,11 @@ inline Operand make_operand(const ae_operand_t* o, int C) {
   r.src = o->src; r.src2 = o->src2; r.bnc = o->bnc; r.scalar = o->scalar; r.mode = o->mode; r.C = C;
   return r;
 }
+inline Operand split_operand(const void* planes, int C) {
+  Operand r; r.src = static_cast<const float*>(planes); r.src2 = nullptr; r.bnc = nullptr; r.scalar = 0.f;
+  r.mode = AE_OP_SPLIT_BF16; r.C = C;
+  return r;
+}
 inline Operand raw_operand(const float* p) {
   Operand r; r.src = p; r.src2 = nullptr; r.bnc = nullptr; r.scalar = 0.f; r.mode = AE_OP_RAW; r.C = 1;
   return r;
@@ -197,11 +202,16 @@ int pack_conv_simt(const float* w, int Cs, int Cb, float* fwd, float* dgrad, cud
 int pack_linear(const float* w, int N, int K, int permC, int permHW, int kind, float* dst, cudaStream_t st);
 int permute_vector(const float* src, int n, int permC, int permHW, float* dst, cudaStream_t st);
 
-// tcgen05 path (tc_gemm.cu)
-size_t tc_packed_bytes(int Cs, int Cb, int nsplit);
-int tc_pack_conv(const float* w, int Cs, int Cb, int nsplit, void* fwd, void* dgrad, cudaStream_t st);
-int tc_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);
-int tc_wgrad(const ColGemm& p, int nsplit, cudaStream_t st);
-bool tc_rowgemm_supported(const RowGemm& p);
+// tcgen05 + TMA path (tma_gemm.cu)
+size_t tma_packed_bytes(int Cs, int Cb, int nsplit);
+int tma_pack_conv(const float* w, int Cs, int Cb, int nsplit, void* fwd, void* dgrad, cudaStream_t st);
+int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit, cudaStream_t st);
+int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);   // p.A: AE_OP_SPLIT_BF16
+bool tma_rowgemm_supported(const RowGemm& p);
+bool tma_wgrad_supported(const Geom& g);
+int tma_wgrad_slices(const Geom& g);
+size_t tma_wgrad_partial_bytes(const Geom& g);
+int tma_wgrad(const Geom& g, const void* big_planes, const void* small_planes, float* dw, float* partial,
+              size_t partial_bytes, int nsplit, cudaStream_t st);
 
 }  // namespace ae

@@ -88,6 +88,8 @@ struct ae_engine {
   float *h = nullptr, *dh = nullptr;  // decoder_input output [B,4,4,256] NHWC and its gradient
   float *t[3] = {}, *dzt[3] = {};     // decoder raw convT outputs / masked gradients
   float *xhat = nullptr;
+  // split-bf16 operand planes of the tcgen05 path (see tma_gemm.cu)
+  void *ae_pl[3] = {}, *ad_pl[2] = {}, *h_pl = nullptr, *dy_pl = nullptr;
   float *z = nullptr, *dz_dec = nullptr, *dz_head = nullptr, *dz_tot = nullptr;
   float *hid_pre = nullptr, *dhid = nullptr, *logits = nullptr, *dlogits = nullptr;
   // packs
@@ -185,6 +187,13 @@ static size_t carve(ae_engine* e, char* base) {
   for (int i = 0; i < 3; ++i) e->t[i] = (float*)take(tsz[i] * 4);
   for (int i = 0; i < 3; ++i) e->dzt[i] = (float*)take(tsz[i] * 4);
   e->xhat = (float*)take(B * 3 * 64 * 64 * 4);
+  if (!e->simt) {
+    const size_t pb = (size_t)2 * e->nsplit;   // bytes per element of a split-bf16 tensor
+    for (int i = 0; i < 3; ++i) e->ae_pl[i] = take(ysz[i] * pb);
+    for (int i = 0; i < 2; ++i) e->ad_pl[i] = take(tsz[i] * pb);
+    e->h_pl = take(B * 4096 * pb);
+    e->dy_pl = take(tsz[2] * pb);
+  }
   e->z = (float*)take(B * L * 4);
   e->dz_dec = (float*)take(B * L * 4);
   e->dz_head = (float*)take(B * L * 4);
@@ -212,7 +221,7 @@ static size_t carve(ae_engine* e, char* base) {
   // packed weights
   for (int i = 0; i < 3; ++i) {
     for (MidLayer* m : {&e->enc_mid[i], &e->dec_mid[i]}) {
-      const size_t bytes = e->simt ? (size_t)9 * m->g.Cb * m->g.Cs * 4 : tc_packed_bytes(m->g.Cs, m->g.Cb, e->nsplit);
+      const size_t bytes = e->simt ? (size_t)9 * m->g.Cb * m->g.Cs * 4 : tma_packed_bytes(m->g.Cs, m->g.Cb, e->nsplit);
       m->pk_bytes = bytes;
       m->pk_fwd = take(bytes);
       m->pk_dgrad = take(bytes);
@@ -232,6 +241,10 @@ static size_t carve(ae_engine* e, char* base) {
       const int I = 9 * m->g.Cb, J = m->g.Cs;
       const int Mrows = (int)(B * m->g.Hs * m->g.Ws);
       upd((size_t)colgemm_default_split(Mrows, I, J) * I * J * 4);
+      if (!e->simt) {
+        // the slice count grows with the batch up to one slice per SM-wave: bound it over all batches <= Bmax
+        upd((size_t)148 * I * J * 4);
+      }
     }
   upd((size_t)colgemm_default_split((int)B, 4096, L) * 4096 * L * 4);
   upd((size_t)colgemm_default_split((int)B, 128, L) * 128 * L * 4);
@@ -253,16 +266,36 @@ static int check_part(const ae_engine* e, int p, bool need_grads) {
   return 0;
 }
 
-static int run_rowgemm(ae_engine* e, RowGemm& r, const void* pk_tc, cudaStream_t st) {
-  if (!e->simt && pk_tc != nullptr && tc_rowgemm_supported(r)) return tc_rowgemm(r, pk_tc, e->nsplit, st);
-  return simt_rowgemm(r, st);
+// Row GEMM of a mid layer.  `a` is the fp32 operand description (transform included); on the tcgen05 path its
+// split-bf16 planes are `planes`: produced here when `split_now`, else already current (written earlier this step).
+static int run_rowgemm(ae_engine* e, RowGemm& r, const Operand& a, void* planes, bool split_now, int64_t a_count,
+                       const void* pk, cudaStream_t st) {
+  if (e->simt) { r.A = a; return simt_rowgemm(r, st); }
+  if (split_now) AE_TRY(tma_split_operand(a, a_count, planes, e->nsplit, st));
+  r.A = split_operand(planes, a.C);
+  return tma_rowgemm(r, pk, e->nsplit, st);
 }
 
-static int run_wgrad(ae_engine* e, ColGemm& c, cudaStream_t st) {
+// Weight gradient of a mid layer: big / small are the fp32 operand descriptions; on the tcgen05 path the planes
+// must already be current.
+static int run_conv_wgrad(ae_engine* e, const Geom& g, const Operand& big, const Operand& small, const void* big_pl,
+                          const void* small_pl, float* dw, cudaStream_t st) {
+  if (!e->simt)
+    return tma_wgrad(g, big_pl, small_pl, dw, e->partial, e->partial_bytes, e->nsplit, st);
+  ColGemm c{};
+  c.gather = 1; c.g = g; c.M = g.B * g.Hs * g.Ws; c.I = 9 * g.Cb; c.J = g.Cs;
+  c.A = big; c.B = small;
+  c.out = dw; c.permC = g.Cb; c.permHW = 9; c.transposed = 1;
   c.splitK = colgemm_default_split(c.M, c.I, c.J);
   c.partial = e->partial;
   AE_CHECK((size_t)c.splitK * c.I * c.J * 4 <= e->partial_bytes, "engine: partial buffer too small");
-  if (!e->simt && c.gather) return tc_wgrad(c, e->nsplit, st);
+  return simt_colgemm(c, st);
+}
+
+static int run_wgrad(ae_engine* e, ColGemm& c, cudaStream_t st) {   // dense layers
+  c.splitK = colgemm_default_split(c.M, c.I, c.J);
+  c.partial = e->partial;
+  AE_CHECK((size_t)c.splitK * c.I * c.J * 4 <= e->partial_bytes, "engine: partial buffer too small");
   return simt_colgemm(c, st);
 }
 
@@ -340,7 +373,7 @@ int ae_engine_pack_weights(ae_engine_t* e, int part, ae_stream_t stream) {
     for (int i = 0; i < 3; ++i) {
       MidLayer& m = mids[i];
       if (e->simt) AE_TRY(pack_conv_simt(p.P(m.w), m.g.Cs, m.g.Cb, (float*)m.pk_fwd, (float*)m.pk_dgrad, st));
-      else AE_TRY(tc_pack_conv(p.P(m.w), m.g.Cs, m.g.Cb, e->nsplit, m.pk_fwd, m.pk_dgrad, st));
+      else AE_TRY(tma_pack_conv(p.P(m.w), m.g.Cs, m.g.Cb, e->nsplit, m.pk_fwd, m.pk_dgrad, st));
     }
   }
   if (part == AE_PART_ENC) {
@@ -384,12 +417,12 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
     RowGemm r{};
     r.family = FAM_FPROP; r.g = m.g; r.g.B = batch;
     r.M = batch * m.g.Hs * m.g.Ws; r.N = m.g.Cs; r.K = 9 * m.g.Cb;
-    r.A = bnrelu_operand(e->y[i], bin.bnc, bin.C);
     r.Bp = (const float*)m.pk_fwd;
     r.epi = training ? bias_stats_epilogue(P.P(m.b), bout.stats_f, bout.C) : store_epilogue(P.P(m.b));
     r.epi.C = bout.C;
     r.out = e->y[i + 1]; r.splitK = 1; r.partial = nullptr;
-    AE_TRY(run_rowgemm(e, r, m.pk_fwd, st));
+    AE_TRY(run_rowgemm(e, r, bnrelu_operand(e->y[i], bin.bnc, bin.C), e->ae_pl[i], true,
+                       (int64_t)batch * bin.count_per_image * bin.C, m.pk_fwd, st));
     AE_TRY(bn_finalize(bout.stats_f, (int64_t)batch * bout.count_per_image, P.P(bout.gamma), P.P(bout.beta),
                        P.rmean(i + 1), P.rvar(i + 1), bout.bnc, bout.C, training, st));
   }
@@ -437,20 +470,18 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     BN& bin = P.bn[i];        // BN of this layer's input (big image)
     BN& bout = P.bn[i + 1];   // BN of this layer's output (small image)
     const int Mrows = batch * m.g.Hs * m.g.Ws;
-    ColGemm c{};
-    c.gather = 1; c.g = m.g; c.g.B = batch; c.M = Mrows; c.I = 9 * m.g.Cb; c.J = m.g.Cs;
-    c.A = bnrelu_operand(e->y[i], bin.bnc, bin.C);
-    c.B = bnbwd_operand(e->dzy[i + 1], e->y[i + 1], bout.bnc, bout.C);
-    c.out = P.G(m.w); c.permC = m.g.Cb; c.permHW = 9; c.transposed = 1;
-    AE_TRY(run_wgrad(e, c, st));
+    Geom g = m.g; g.B = batch;
+    const Operand a_big = bnrelu_operand(e->y[i], bin.bnc, bin.C);                          // planes: ae_pl[i] (forward)
+    const Operand dy_small = bnbwd_operand(e->dzy[i + 1], e->y[i + 1], bout.bnc, bout.C);   // planes: dy_pl (now)
+    if (!e->simt) AE_TRY(tma_split_operand(dy_small, (int64_t)Mrows * m.g.Cs, e->dy_pl, e->nsplit, st));
+    AE_TRY(run_conv_wgrad(e, g, a_big, dy_small, e->ae_pl[i], e->dy_pl, P.G(m.w), st));
     AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cs * 4, st));   // bias feeding a training BN: exact zero gradient
     RowGemm r{};
-    r.family = FAM_DGRAD; r.g = m.g; r.g.B = batch; r.M = Mrows; r.N = m.g.Cb; r.K = 0;
-    r.A = bnbwd_operand(e->dzy[i + 1], e->y[i + 1], bout.bnc, bout.C);
+    r.family = FAM_DGRAD; r.g = g; r.M = Mrows; r.N = m.g.Cb; r.K = 0;
     r.Bp = (const float*)m.pk_dgrad;
     r.epi = relubwd_epilogue(e->y[i], bin.bnc, bin.stats_b, bin.C);
     r.out = e->dzy[i]; r.splitK = 1;
-    AE_TRY(run_rowgemm(e, r, m.pk_dgrad, st));
+    AE_TRY(run_rowgemm(e, r, dy_small, e->dy_pl, false, 0, m.pk_dgrad, st));
     AE_TRY(bn_bwd_reduce(bin.stats_b, (int64_t)batch * bin.count_per_image, P.P(bin.gamma), bin.bnc, P.G(bin.gamma),
                          P.G(bin.beta), bin.C, st));
   }
@@ -488,13 +519,13 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
     BN& bout = P.bn[i];
     RowGemm r{};
     r.family = FAM_DGRAD; r.g = m.g; r.g.B = batch; r.M = batch * m.g.Hs * m.g.Ws; r.N = m.g.Cb; r.K = 0;
-    r.A = i == 0 ? raw_operand(e->h) : bnrelu_operand(e->t[i - 1], P.bn[i - 1].bnc, P.bn[i - 1].C);
-    if (i == 0) r.A.C = m.g.Cs;
+    Operand a = i == 0 ? raw_operand(e->h) : bnrelu_operand(e->t[i - 1], P.bn[i - 1].bnc, P.bn[i - 1].C);
+    if (i == 0) a.C = m.g.Cs;
     r.Bp = (const float*)m.pk_dgrad;
     r.epi = training ? bias_stats_epilogue(P.P(m.b), bout.stats_f, bout.C) : store_epilogue(P.P(m.b));
     r.epi.C = bout.C;
     r.out = e->t[i]; r.splitK = 1;
-    AE_TRY(run_rowgemm(e, r, m.pk_dgrad, st));
+    AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], true, (int64_t)r.M * m.g.Cs, m.pk_dgrad, st));
     AE_TRY(bn_finalize(bout.stats_f, (int64_t)batch * bout.count_per_image, P.P(bout.gamma), P.P(bout.beta), P.rmean(i),
                        P.rvar(i), bout.bnc, bout.C, training, st));
   }
@@ -527,23 +558,20 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     MidLayer& m = e->dec_mid[i];
     BN& bout = P.bn[i];  // BN after this layer's output (big image)
     const int Mrows = batch * m.g.Hs * m.g.Ws;
-    const Operand small = i == 0 ? raw_operand(e->h) : bnrelu_operand(e->t[i - 1], P.bn[i - 1].bnc, P.bn[i - 1].C);
-    ColGemm c{};
-    c.gather = 1; c.g = m.g; c.g.B = batch; c.M = Mrows; c.I = 9 * m.g.Cb; c.J = m.g.Cs;
-    c.A = bnbwd_operand(e->dzt[i], e->t[i], bout.bnc, bout.C);
-    c.B = small;
-    if (i == 0) c.B.C = m.g.Cs;
-    c.out = P.G(m.w); c.permC = m.g.Cb; c.permHW = 9; c.transposed = 1;
-    AE_TRY(run_wgrad(e, c, st));
+    Operand small = i == 0 ? raw_operand(e->h) : bnrelu_operand(e->t[i - 1], P.bn[i - 1].bnc, P.bn[i - 1].C);
+    if (i == 0) small.C = m.g.Cs;                                                   // planes: h_pl / ad_pl[i-1] (forward)
+    const Operand dy_big = bnbwd_operand(e->dzt[i], e->t[i], bout.bnc, bout.C);     // planes: dy_pl (now)
+    Geom g = m.g; g.B = batch;
+    if (!e->simt) AE_TRY(tma_split_operand(dy_big, (int64_t)Mrows * 4 * m.g.Cb, e->dy_pl, e->nsplit, st));
+    AE_TRY(run_conv_wgrad(e, g, dy_big, small, e->dy_pl, i == 0 ? e->h_pl : e->ad_pl[i - 1], P.G(m.w), st));
     AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cb * 4, st));
     RowGemm r{};
-    r.family = FAM_FPROP; r.g = m.g; r.g.B = batch; r.M = Mrows; r.N = m.g.Cs; r.K = 9 * m.g.Cb;
-    r.A = bnbwd_operand(e->dzt[i], e->t[i], bout.bnc, bout.C);
+    r.family = FAM_FPROP; r.g = g; r.M = Mrows; r.N = m.g.Cs; r.K = 9 * m.g.Cb;
     r.Bp = (const float*)m.pk_fwd;
     if (i == 0) { r.epi = store_epilogue(); r.epi.C = m.g.Cs; r.out = e->dh; }
     else { BN& bin = P.bn[i - 1]; r.epi = relubwd_epilogue(e->t[i - 1], bin.bnc, bin.stats_b, bin.C); r.out = e->dzt[i - 1]; }
     r.splitK = 1;
-    AE_TRY(run_rowgemm(e, r, m.pk_fwd, st));
+    AE_TRY(run_rowgemm(e, r, dy_big, e->dy_pl, false, 0, m.pk_fwd, st));
     if (i > 0) {
       BN& bin = P.bn[i - 1];
       AE_TRY(bn_bwd_reduce(bin.stats_b, (int64_t)batch * bin.count_per_image, P.P(bin.gamma), bin.bnc, P.G(bin.gamma),

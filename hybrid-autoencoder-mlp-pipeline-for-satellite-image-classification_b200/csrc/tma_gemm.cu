@@ -1,0 +1,658 @@
+// TMA-fed tcgen05 / TMEM implicit-GEMM kernels for the six 32..256-channel stride-2 layers (sm_100a only).
+//
+// Activation operands are "split-bf16" NHWC tensors: [nsplit][B][H][W][C] bf16, plane 0 = round-to-nearest bf16
+// of the fp32 value, plane 1 (AE_PREC_FP32 only) = bf16 of the remainder.  They are produced once per tensor by
+// k_split_operand (which also applies BatchNorm+ReLU / BatchNorm-backward), so the GEMM kernels contain no
+// CUDA-core operand math: one thread issues 5-d TMA tile loads (cp.async.bulk.tensor) straight into the
+// SWIZZLE_128B / SWIZZLE_64B shared-memory layout tcgen05.mma reads, one thread issues the MMAs, four warps run
+// the epilogue out of tensor memory.
+//
+//   row GEMM   D[128 pixels x NT channels] = A[128 x K] * W[NT x K]^T
+//       FAM_FPROP (big -> small): Conv2d forward / ConvTranspose2d data gradient.  K = 9 taps x Cb.  The stride-2
+//                  gather is expressed as four tensor maps, one per (row, column) parity of the big image, each a
+//                  plain unit-stride lattice; tap (ky,kx) is a box of one parity lattice shifted by -1 or 0 and
+//                  the zero padding is TMA's out-of-bounds fill.
+//       FAM_DGRAD (small -> big, 4 output-parity phases): ConvTranspose2d forward / Conv2d data gradient.
+//                  K = (1,2,2,4) taps x Cs; every tap is a box of the small image shifted by 0 or +1.
+//   weight gradient  dW[(tap,cb) x cs] = sum over small pixels: A = gathered big image, B = small image, both
+//       MN-major operands (the reduction index is the pixel = the row of the TMA box), split over pixel slices,
+//       partial tiles reduced in a fixed order (deterministic).
+//
+// AE_PREC_FP32 issues hi*hi + hi*lo + lo*hi (3 MMAs per k-step, fp32 accumulate): ~2^-17 relative error per product.
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace ae {
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps (host)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// Lattice of an NHWC split-bf16 tensor: pixels (y0 + sy*j, x0 + sx*i), j < nH, i < nW, of a [B][H][W][C] image.
+// Box = (kc channels, bx, by, bn, nsplit).
+static int encode_map(CUtensorMap* map, const void* planes, int B, int H, int W, int C, int nsplit, int y0, int x0,
+                      int sy, int sx, int nH, int nW, int kc, int bx, int by, int bn) {
+  EncodeTiledFn fn = encode_fn();
+  AE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const char* base = static_cast<const char*>(planes) + ((size_t)y0 * W + x0) * C * 2;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)nW, (cuuint64_t)nH, (cuuint64_t)B, (cuuint64_t)nsplit};
+  cuuint64_t strides[4] = {(cuuint64_t)sx * C * 2, (cuuint64_t)sy * W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)B * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn, (cuuint32_t)nsplit};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = kc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  AE_CHECK(kc * 2 == 128 || kc * 2 == 64, "encode_map: box of %d channels is neither 64 nor 128 bytes", kc);
+  AE_CHECK(((uintptr_t)base & 15) == 0, "encode_map: tensor base must be 16-byte aligned");
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<char*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AE_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (C=%d W=%d H=%d B=%d box %d,%d,%d,%d)", (int)r, C,
+           nW, nH, B, kc, bx, by, bn);
+  return 0;
+}
+
+// pixel box of `rows` consecutive small pixels (row-major over n, y, x): bx * by * bn == rows
+static void pixel_box(int Hs, int Ws, int rows, int* bx, int* by, int* bn) {
+  *bx = Ws < rows ? Ws : rows;
+  int r = rows / *bx;
+  *by = Hs < r ? Hs : r;
+  *bn = r / *by;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_split_operand: fp32 NHWC (+ operand transform) -> split-bf16 planes
+// ---------------------------------------------------------------------------------------------
+template <int NSPLIT>
+__global__ void __launch_bounds__(256) k_split_operand(Operand op, int64_t n8, int64_t plane_elems,
+                                                      __nv_bfloat16* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const size_t off = (size_t)i * 8;
+    const int c = (int)(off % (size_t)op.C);
+    const float4 a = load_operand4(op, off, c, true);
+    const float4 b = load_operand4(op, off + 4, c + 4, true);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 hi;
+    hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]); hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + off) = hi;
+    if (NSPLIT == 2) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+      uint4 lo;
+      lo.x = pack_bf16x2(r[0], r[1]); lo.y = pack_bf16x2(r[2], r[3]); lo.z = pack_bf16x2(r[4], r[5]); lo.w = pack_bf16x2(r[6], r[7]);
+      *reinterpret_cast<uint4*>(dst + plane_elems + off) = lo;
+    }
+  }
+}
+
+int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit, cudaStream_t st) {
+  AE_CHECK(count % 8 == 0 && op.C % 8 == 0, "split_operand: count=%lld and C=%d must be multiples of 8", (long long)count, op.C);
+  AE_CHECK(op.mode == AE_OP_RAW || op.mode == AE_OP_BNRELU || op.mode == AE_OP_BNBWD, "split_operand: unsupported operand mode %d", op.mode);
+  AE_CHECK(((uintptr_t)planes & 15) == 0, "split_operand: destination must be 16-byte aligned");
+  const int64_t n8 = count / 8;
+  int64_t blocks = (n8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  if (nsplit == 2) k_split_operand<2><<<(int)blocks, 256, 0, st>>>(op, n8, count, (__nv_bfloat16*)planes);
+  else k_split_operand<1><<<(int)blocks, 256, 0, st>>>(op, n8, count, (__nv_bfloat16*)planes);
+  AE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row GEMM kernel
+// ---------------------------------------------------------------------------------------------
+static constexpr int RG_THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2..5: epilogue
+
+struct alignas(64) TmaRow {
+  CUtensorMap amap[4];      // FPROP: parity lattices (py*2+px) of the big image; DGRAD: [0] = small image
+  const uint8_t* wtiles;    // packed weight tiles
+  Geom g;
+  Epilogue epi;
+  float* out;
+  int M, N;
+  int cpt;                  // K chunks per tap (C / KC)
+  int wchunks;              // K chunks per n-tile in the weight pack (all taps / all phases)
+  int bx, by, bn;           // pixel box of one 128-row tile
+};
+
+template <int FAMILY, int NT, int KC, int NSPLIT, int STAGES>
+__global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constant__ TmaRow q) {
+  constexpr int ROWB = KC * 2;                                // bytes per shared-memory row
+  constexpr uint32_t A_PLANE = TILE_M * ROWB;
+  constexpr uint32_t B_PLANE = NT * ROWB;
+  constexpr uint32_t A_BYTES = NSPLIT * A_PLANE, B_BYTES = NSPLIT * B_PLANE;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t SBO = 8 * ROWB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float sStat[2][NT];
+
+  const Geom g = q.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TILE_M;
+  const int ntile = blockIdx.y;
+  int py = 0, px = 0, kc_off = 0, nkc;
+  if (FAMILY == FAM_DGRAD) {
+    const int phase = blockIdx.z;
+    py = phase >> 1; px = phase & 1;
+    nkc = (1 + py) * (1 + px) * q.cpt;
+    kc_off = (phase == 0 ? 0 : phase == 1 ? 1 : phase == 2 ? 3 : 5) * q.cpt;
+  } else {
+    nkc = 9 * q.cpt;
+  }
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar0 + 8u * (2 * STAGES);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (tid >= 64 && tid < 64 + NT) { sStat[0][tid - 64] = 0.f; sStat[1][tid - 64] = 0.f; }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      // tile origin in the small image
+      const int P = g.Hs * g.Ws;
+      const int n0 = m0 >> (g.lHs + g.lWs);
+      const int y0 = (m0 & (P - 1)) >> g.lWs;
+      const uint8_t* wsrc = q.wtiles + ((size_t)ntile * q.wchunks + kc_off) * B_BYTES;
+      for (int it = 0; it < nkc; ++it) {
+        const int s = it % STAGES, round = it / STAGES;
+        if (round > 0) mbar_wait(empty_bar(s), (round - 1) & 1);
+        const uint32_t a_dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+        const int tap = it / q.cpt, c0 = (it - tap * q.cpt) * KC;
+        if (FAMILY == FAM_FPROP) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const int pmap = ((ky + 1) & 1) * 2 + ((kx + 1) & 1);       // parity lattice of source row 2*oy-1+ky
+          tma_load_5d(a_dst, &q.amap[pmap], c0, (kx == 0) ? -1 : 0, y0 + ((ky == 0) ? -1 : 0), n0, 0, full_bar(s));
+        } else {
+          const int a = tap / (1 + px), b = tap - a * (1 + px);
+          const int dy = (py && a == 0) ? 1 : 0, dx = (px && b == 0) ? 1 : 0;   // source = (y + dy, x + dx)
+          tma_load_5d(a_dst, &q.amap[0], c0, dx, y0 + dy, n0, 0, full_bar(s));
+        }
+        bulk_copy_g2s(a_dst + A_BYTES, wsrc + (size_t)it * B_BYTES, B_BYTES, full_bar(s));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(NT, 0, 0);
+      for (int it = 0; it < nkc; ++it) {
+        const int s = it % STAGES, round = it / STAGES;
+        mbar_wait(full_bar(s), round & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t b0 = a0 + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KC / 16; ++kk) {
+          const uint64_t ah = make_desc(a0 + kk * 32, 16, SBO, ROWB), bh = make_desc(b0 + kk * 32, 16, SBO, ROWB);
+          umma_bf16(tmem_base, ah, bh, idesc, (it | kk) != 0);
+          if (NSPLIT == 2) {
+            const uint64_t al = make_desc(a0 + A_PLANE + kk * 32, 16, SBO, ROWB);
+            const uint64_t bl = make_desc(b0 + B_PLANE + kk * 32, 16, SBO, ROWB);
+            umma_bf16(tmem_base, ah, bl, idesc, 1);
+            umma_bf16(tmem_base, al, bh, idesc, 1);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5; warp w owns TMEM lanes 32*(w%4) ..) =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < q.M;
+    const Epilogue e = q.epi;
+    size_t orow = 0;
+    if (row_ok) {
+      if (FAMILY == FAM_DGRAD) {
+        const int x = m & (g.Ws - 1), y = (m >> g.lWs) & (g.Hs - 1), nn = m >> (g.lWs + g.lHs);
+        orow = (((size_t)nn * (2 * g.Hs) + 2 * y + py) * (2 * g.Ws) + 2 * x + px) * q.N;
+      } else {
+        orow = (size_t)m * q.N;
+      }
+    }
+#pragma unroll 1
+    for (int col0 = 0; col0 < NT; col0 += 32) {
+      const int n = ntile * NT + col0;                 // global output channel
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
+      float s2[32];
+      if (e.mode == AE_EPI_RELUBWD_STATS) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok) yv = __ldg(reinterpret_cast<const float4*>(e.y + orow + n) + j4);
+          const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = (n + j4 * 4 + j) % e.C;
+            const float z = fmaf(ya[j], __ldg(e.bnc + AE_BNC_SCALE * e.C + ch), __ldg(e.bnc + AE_BNC_SHIFT * e.C + ch));
+            const float d = (row_ok && z > 0.f) ? v[j4 * 4 + j] : 0.f;
+            v[j4 * 4 + j] = d;
+            s2[j4 * 4 + j] = d * ((ya[j] - __ldg(e.bnc + AE_BNC_MEAN * e.C + ch)) * __ldg(e.bnc + AE_BNC_RSTD * e.C + ch));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float d = v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f);
+          d = row_ok ? d : 0.f;
+          v[j] = d;
+          s2[j] = d * d;
+        }
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          reinterpret_cast<float4*>(q.out + orow + n)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+      }
+      if (e.mode != AE_EPI_STORE && e.stats) {
+        const float a = warp_colsum32_tc(v, lane);
+        const float b = warp_colsum32_tc(s2, lane);
+        atomicAdd(&sStat[0][col0 + lane], a);
+        atomicAdd(&sStat[1][col0 + lane], b);
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int et = tid - 64;
+    if (e.mode != AE_EPI_STORE && e.stats && et < NT) {
+      const int ch = (ntile * NT + et) % e.C;
+      atomicAdd(e.stats + ch, (double)sStat[0][et]);
+      atomicAdd(e.stats + e.C + ch, (double)sStat[1][et]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, NT);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: w [Cs][Cb][3][3] fp32 -> swizzled bf16 (hi[, lo]) tiles for both row-GEMM orientations.
+// Tile (n_tile, chunk): [plane][NT rows][KC*2 bytes]; element (r, j) of a tile at
+//   r*ROWB + ((chunk16 ^ swz(r)) << 4) + (j & 7)*2,  chunk16 = j >> 3,
+//   swz(r) = r & 7 for 128-byte rows (SWIZZLE_128B), (r >> 1) & 3 for 64-byte rows (SWIZZLE_64B).
+// fwd  : n = cs, K order (tap, cb), KC = min(Cb, 64).   dgrad: n = cb, K order (phase-stacked tap slot, cs), KC = 64.
+// ---------------------------------------------------------------------------------------------
+static inline int nt_for(int n) { return n >= 64 ? 64 : 32; }
+static inline int kc_fwd(int Cb) { return Cb >= 64 ? 64 : 32; }
+
+__global__ void k_tma_pack_conv(const float* __restrict__ w, int Cs, int Cb, int nsplit, uint8_t* __restrict__ fwd,
+                                uint8_t* __restrict__ dgrad) {
+  const int KCf = Cb >= 64 ? 64 : 32, NTf = Cs >= 64 ? 64 : 32;
+  const int NTd = Cb >= 64 ? 64 : 32;
+  const int nf = Cs * 9 * Cb, nd = Cb * 9 * Cs;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nf + nd; idx += gridDim.x * blockDim.x) {
+    float v;
+    uint8_t* base;
+    int r, j, NT, KC;
+    size_t tile;
+    if (idx < nf) {
+      const int k = idx % (9 * Cb), n = idx / (9 * Cb);   // n = cs, k = tap*Cb + cb
+      const int tap = k / Cb, cb = k - tap * Cb;
+      v = w[((size_t)n * Cb + cb) * 9 + tap];
+      KC = KCf; NT = NTf;
+      const int kc = k / KC; j = k - kc * KC;
+      r = n % NT; tile = (size_t)(n / NT) * (9 * Cb / KC) + kc; base = fwd;
+    } else {
+      const int i2 = idx - nf;
+      const int k = i2 % (9 * Cs), n = i2 / (9 * Cs);     // n = cb, k = slot*Cs + cs
+      const int slot = k / Cs, cs = k - slot * Cs;        // slot 0: phase 0; 1-2: phase 1; 3-4: phase 2; 5-8: phase 3
+      int ky, kx;
+      if (slot == 0) { ky = 1; kx = 1; }
+      else if (slot <= 2) { ky = 1; kx = slot == 1 ? 0 : 2; }
+      else if (slot <= 4) { ky = slot == 3 ? 0 : 2; kx = 1; }
+      else { const int t = slot - 5; ky = (t >> 1) ? 2 : 0; kx = (t & 1) ? 2 : 0; }
+      v = w[((size_t)cs * Cb + n) * 9 + ky * 3 + kx];
+      KC = 64; NT = NTd;
+      const int kc = k / KC; j = k - kc * KC;
+      r = n % NT; tile = (size_t)(n / NT) * (9 * Cs / KC) + kc; base = dgrad;
+    }
+    const int rowb = KC * 2;
+    const int swz = rowb == 128 ? (r & 7) : ((r >> 1) & 3);
+    const size_t tile_bytes = (size_t)nsplit * NT * rowb;
+    const size_t off = tile * tile_bytes + (size_t)r * rowb + (size_t)((((j >> 3) ^ swz) << 4) + (j & 7) * 2);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+    if (nsplit == 2) *reinterpret_cast<__nv_bfloat16*>(base + off + (size_t)NT * rowb) = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+size_t tma_packed_bytes(int Cs, int Cb, int nsplit) { return (size_t)9 * Cs * Cb * 2 * nsplit + 1024; }
+
+int tma_pack_conv(const float* w, int Cs, int Cb, int nsplit, void* fwd, void* dgrad, cudaStream_t st) {
+  AE_CHECK(Cs % 64 == 0 && Cb % 32 == 0, "tma_pack_conv: Cs=%d must be a multiple of 64 and Cb=%d of 32", Cs, Cb);
+  AE_CHECK((((uintptr_t)fwd | (uintptr_t)dgrad) & 15) == 0, "tma_pack_conv: packed buffers must be 16-byte aligned");
+  const int total = 2 * 9 * Cs * Cb;
+  int blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_tma_pack_conv<<<blocks, 256, 0, st>>>(w, Cs, Cb, nsplit, (uint8_t*)fwd, (uint8_t*)dgrad);
+  AE_LAUNCH_CHECK();
+  return 0;
+}
+
+bool tma_rowgemm_supported(const RowGemm& p) {
+  if (!is_pow2(p.g.Hs) || !is_pow2(p.g.Ws) || p.g.Ws > 128 || p.g.Hs * p.g.Ws < 8) return false;
+  if (p.family == FAM_FPROP) return (p.g.Cb == 32 || p.g.Cb % 64 == 0) && p.N % 32 == 0 && p.splitK <= 1;
+  if (p.family == FAM_DGRAD) return p.g.Cs % 64 == 0 && p.N % 32 == 0;
+  return false;
+}
+
+template <int FAMILY, int NT, int KC, int NSPLIT, int STAGES>
+static int launch_row(const TmaRow& q, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * NSPLIT * (TILE_M * KC * 2 + NT * KC * 2) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AE_CUDA(cudaFuncSetAttribute(k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES><<<grid, RG_THREADS, smem, st>>>(q);
+  AE_LAUNCH_CHECK();
+  return 0;
+}
+
+// p.A.src must point to the split-bf16 planes of the A image (AE_OP_SPLIT_BF16)
+int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st) {
+  AE_CHECK(tma_rowgemm_supported(p), "tma_rowgemm: unsupported shape");
+  AE_CHECK(p.A.mode == AE_OP_SPLIT_BF16, "tma_rowgemm: the A operand must be split-bf16 planes (ae_split_operand)");
+  AE_CHECK(((uintptr_t)packed & 15) == 0, "tma_rowgemm: packed weights must be 16-byte aligned");
+  TmaRow q;
+  memset(&q, 0, sizeof(q));
+  q.wtiles = (const uint8_t*)packed;
+  q.g = p.g; q.epi = p.epi; q.out = p.out; q.M = p.M; q.N = p.N;
+  const Geom& g = p.g;
+  pixel_box(g.Hs, g.Ws, TILE_M, &q.bx, &q.by, &q.bn);
+  const int NT = nt_for(p.N);
+  dim3 grid((p.M + TILE_M - 1) / TILE_M, p.N / NT, 1);
+  if (p.family == FAM_FPROP) {
+    const int KC = kc_fwd(g.Cb);
+    q.cpt = g.Cb / KC; q.wchunks = 9 * q.cpt;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        AE_TRY(encode_map(&q.amap[py * 2 + px], p.A.src, g.B, 2 * g.Hs, 2 * g.Ws, g.Cb, nsplit, py, px, 2, 2, g.Hs, g.Ws, KC,
+                          q.bx, q.by, q.bn));
+    if (KC == 64) {
+      if (NT == 64) return nsplit == 2 ? launch_row<FAM_FPROP, 64, 64, 2, 2>(q, grid, st) : launch_row<FAM_FPROP, 64, 64, 1, 4>(q, grid, st);
+      return nsplit == 2 ? launch_row<FAM_FPROP, 32, 64, 2, 2>(q, grid, st) : launch_row<FAM_FPROP, 32, 64, 1, 4>(q, grid, st);
+    }
+    if (NT == 64) return nsplit == 2 ? launch_row<FAM_FPROP, 64, 32, 2, 4>(q, grid, st) : launch_row<FAM_FPROP, 64, 32, 1, 6>(q, grid, st);
+    return nsplit == 2 ? launch_row<FAM_FPROP, 32, 32, 2, 4>(q, grid, st) : launch_row<FAM_FPROP, 32, 32, 1, 6>(q, grid, st);
+  }
+  q.cpt = g.Cs / 64; q.wchunks = 9 * q.cpt;
+  AE_TRY(encode_map(&q.amap[0], p.A.src, g.B, g.Hs, g.Ws, g.Cs, nsplit, 0, 0, 1, 1, g.Hs, g.Ws, 64, q.bx, q.by, q.bn));
+  grid.z = 4;
+  if (NT == 64) return nsplit == 2 ? launch_row<FAM_DGRAD, 64, 64, 2, 2>(q, grid, st) : launch_row<FAM_DGRAD, 64, 64, 1, 4>(q, grid, st);
+  return nsplit == 2 ? launch_row<FAM_DGRAD, 32, 64, 2, 2>(q, grid, st) : launch_row<FAM_DGRAD, 32, 64, 1, 4>(q, grid, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight-gradient kernel: D[(tap,cb) tile of 128][cs] += sum over a slice of small pixels
+// ---------------------------------------------------------------------------------------------
+struct alignas(64) TmaWgrad {
+  CUtensorMap bigmap[4];    // parity lattices of the big image, box = 64 pixels x KCA channels
+  CUtensorMap smallmap;     // small image, box = 64 pixels x 64 channels
+  Geom g;
+  float* partial;           // [slices][9*Cb][Cs]
+  int chunks;               // 64-pixel chunks in total
+  int chunks_per_slice;
+  int I;                    // 9*Cb
+};
+
+// KCA = channels per A group (64, or 32 when Cb == 32); NB = Cs (64/128/256)
+template <int KCA, int NB, int NSPLIT, int STAGES>
+__global__ void __launch_bounds__(RG_THREADS) k_tma_wgrad(const __grid_constant__ TmaWgrad q) {
+  constexpr int KPIX = 64;                                   // pixels (reduction rows) per stage
+  constexpr int ROWA = KCA * 2;                              // bytes per A row
+  constexpr int GA = 128 / KCA;                              // A groups per 128-row tile
+  constexpr int GB = NB / 64;
+  constexpr uint32_t A_GROUP = KPIX * ROWA;                  // one TMA box of one plane
+  constexpr uint32_t A_PLANE = GA * A_GROUP;                 // = 16 KB
+  constexpr uint32_t B_GROUP = KPIX * 128;
+  constexpr uint32_t B_PLANE = GB * B_GROUP;
+  constexpr uint32_t A_BYTES = NSPLIT * A_PLANE, B_BYTES = NSPLIT * B_PLANE;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+
+  const Geom g = q.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.x, slice = blockIdx.y;
+  const int ch_beg = slice * q.chunks_per_slice;
+  const int ch_end = min(q.chunks, ch_beg + q.chunks_per_slice);
+  const int nch = max(0, ch_end - ch_beg);
+  // groups of this tile: linear group index gi -> (tap, c0)
+  const int gpt = g.Cb / KCA;                                // groups per tap
+  const int gi0 = mt * GA;
+  int ngroups = 9 * gpt - gi0;
+  if (ngroups > GA) ngroups = GA;
+
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar0 + 8u * (2 * STAGES);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), NB);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int P = g.Hs * g.Ws;
+      for (int it = 0; it < nch; ++it) {
+        const int s = it % STAGES, round = it / STAGES;
+        if (round > 0) mbar_wait(empty_bar(s), (round - 1) & 1);
+        const uint32_t a_dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        mbar_arrive_expect_tx(full_bar(s), (uint32_t)ngroups * NSPLIT * A_GROUP + B_BYTES);
+        const int p0 = (ch_beg + it) * KPIX;                 // first small pixel of the chunk
+        const int n0 = p0 >> (g.lHs + g.lWs);
+        const int y0 = (p0 & (P - 1)) >> g.lWs;
+        const int x0 = p0 & (g.Ws - 1);                      // non-zero only when Ws > 64 (not used by the model)
+        for (int gq = 0; gq < ngroups; ++gq) {
+          const int gi = gi0 + gq;
+          const int tap = gi / gpt, c0 = (gi - tap * gpt) * KCA;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const int pmap = ((ky + 1) & 1) * 2 + ((kx + 1) & 1);
+          // one box = [plane][64 pixels][ROWA] = NSPLIT * A_GROUP bytes: group gq lands at a_dst + gq * NSPLIT * A_GROUP
+          tma_load_5d(a_dst + gq * NSPLIT * A_GROUP, &q.bigmap[pmap], c0, x0 + ((kx == 0) ? -1 : 0),
+                      y0 + ((ky == 0) ? -1 : 0), n0, 0, full_bar(s));
+        }
+        for (int gq = 0; gq < GB; ++gq)
+          tma_load_5d(a_dst + A_BYTES + gq * NSPLIT * B_GROUP, &q.smallmap, gq * 64, x0, y0, n0, 0, full_bar(s));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(NB, 1, 1);
+      for (int it = 0; it < nch; ++it) {
+        const int s = it % STAGES, round = it / STAGES;
+        mbar_wait(full_bar(s), round & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t b0 = a0 + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KPIX / 16; ++kk) {
+          // 16 pixels = two 8-row groups: advance by 16 rows.  Shared layout per operand: [group][plane][64 rows][row bytes],
+          // so consecutive M/N groups of one plane are NSPLIT * GROUP bytes apart (the descriptor's leading byte offset).
+          const uint64_t ah = make_desc(a0 + kk * 16 * ROWA, NSPLIT * A_GROUP, 8 * ROWA, ROWA);
+          const uint64_t bh = make_desc(b0 + kk * 16 * 128, NSPLIT * B_GROUP, 1024, 128);
+          umma_bf16(tmem_base, ah, bh, idesc, (it | kk) != 0);
+          if (NSPLIT == 2) {
+            const uint64_t al = make_desc(a0 + A_GROUP + kk * 16 * ROWA, NSPLIT * A_GROUP, 8 * ROWA, ROWA);
+            const uint64_t bl = make_desc(b0 + B_GROUP + kk * 16 * 128, NSPLIT * B_GROUP, 1024, 128);
+            umma_bf16(tmem_base, ah, bl, idesc, 1);
+            umma_bf16(tmem_base, al, bh, idesc, 1);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const int i = mt * 128 + row;                            // (tap, cb) index
+    float* dst = q.partial + ((size_t)slice * q.I + i) * NB;
+    if (nch > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int col0 = 0; col0 < NB; col0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
+        if (i < q.I) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            reinterpret_cast<float4*>(dst + col0)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+      }
+    } else if (i < q.I) {
+      for (int c = 0; c < NB; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, NB);
+  }
+}
+
+// dw[cs][cb][tap] = sum_s partial[s][tap*Cb + cb][cs]   (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int slices, int I, int J, int Cb,
+                                                      float* __restrict__ dw) {
+  const int n4 = I * J / 4;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += gridDim.x * blockDim.x) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(partial) + idx);
+    for (int k = 1; k < slices; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)k * I * J) + idx);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const int e = idx * 4;
+    const int i = e / J, j = e - i * J;
+    const int tap = i / Cb, cb = i - tap * Cb;
+    const size_t o = ((size_t)j * Cb + cb) * 9 + tap;
+    const size_t js = (size_t)Cb * 9;
+    dw[o] = s.x; dw[o + js] = s.y; dw[o + 2 * js] = s.z; dw[o + 3 * js] = s.w;
+  }
+}
+
+bool tma_wgrad_supported(const Geom& g) {
+  if (!is_pow2(g.Hs) || !is_pow2(g.Ws) || g.Ws > 64 || g.Hs * g.Ws < 8) return false;
+  return (g.Cb == 32 || g.Cb == 64 || g.Cb == 128) && (g.Cs == 64 || g.Cs == 128 || g.Cs == 256);
+}
+
+int tma_wgrad_slices(const Geom& g) {
+  const int chunks = (g.B * g.Hs * g.Ws + 63) / 64;
+  const int mtiles = (9 * g.Cb + 127) / 128;
+  int s = (148 + mtiles - 1) / mtiles;
+  if (s > chunks) s = chunks;
+  if (s < 1) s = 1;
+  // every slice non-empty
+  const int per = (chunks + s - 1) / s;
+  return (chunks + per - 1) / per;
+}
+
+size_t tma_wgrad_partial_bytes(const Geom& g) { return (size_t)tma_wgrad_slices(g) * 9 * g.Cb * g.Cs * sizeof(float); }
+
+template <int KCA, int NB, int NSPLIT, int STAGES>
+static int launch_wgrad(const TmaWgrad& q, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * NSPLIT * (128 * 64 * 2 + NB * 64 * 2) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AE_CUDA(cudaFuncSetAttribute(k_tma_wgrad<KCA, NB, NSPLIT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_tma_wgrad<KCA, NB, NSPLIT, STAGES><<<grid, RG_THREADS, smem, st>>>(q);
+  AE_LAUNCH_CHECK();
+  return 0;
+}
+
+// big / small: split-bf16 planes of the (transformed) big and small images; dw: [Cs][Cb][3][3] fp32
+int tma_wgrad(const Geom& g, const void* big, const void* small, float* dw, float* partial, size_t partial_bytes, int nsplit,
+              cudaStream_t st) {
+  AE_CHECK(tma_wgrad_supported(g), "tma_wgrad: unsupported shape (Cb=%d Cs=%d Hs=%d Ws=%d)", g.Cb, g.Cs, g.Hs, g.Ws);
+  const int slices = tma_wgrad_slices(g);
+  AE_CHECK(partial != nullptr && partial_bytes >= (size_t)slices * 9 * g.Cb * g.Cs * 4, "tma_wgrad: partial buffer too small");
+  TmaWgrad q;
+  memset(&q, 0, sizeof(q));
+  q.g = g; q.partial = partial; q.I = 9 * g.Cb;
+  q.chunks = (g.B * g.Hs * g.Ws + 63) / 64;
+  q.chunks_per_slice = (q.chunks + slices - 1) / slices;
+  int bx, by, bn;
+  pixel_box(g.Hs, g.Ws, 64, &bx, &by, &bn);
+  const int KCA = g.Cb >= 64 ? 64 : 32;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      AE_TRY(encode_map(&q.bigmap[py * 2 + px], big, g.B, 2 * g.Hs, 2 * g.Ws, g.Cb, nsplit, py, px, 2, 2, g.Hs, g.Ws, KCA, bx, by, bn));
+    }
+  AE_TRY(encode_map(&q.smallmap, small, g.B, g.Hs, g.Ws, g.Cs, nsplit, 0, 0, 1, 1, g.Hs, g.Ws, 64, bx, by, bn));
+  dim3 grid((q.I + 127) / 128, slices, 1);
+  int rc;
+#define AE_WG(KCA_, NB_)                                                                                            \
+  (nsplit == 2 ? launch_wgrad<KCA_, NB_, 2, (NB_ == 256 ? 2 : NB_ == 128 ? 3 : 4)>(q, grid, st)                      \
+               : launch_wgrad<KCA_, NB_, 1, (NB_ == 256 ? 4 : NB_ == 128 ? 5 : 6)>(q, grid, st))
+  if (KCA == 64) rc = g.Cs == 64 ? AE_WG(64, 64) : g.Cs == 128 ? AE_WG(64, 128) : AE_WG(64, 256);
+  else rc = g.Cs == 64 ? AE_WG(32, 64) : g.Cs == 128 ? AE_WG(32, 128) : AE_WG(32, 256);
+#undef AE_WG
+  AE_TRY(rc);
+  const int n4 = q.I * g.Cs / 4;
+  int blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  k_wgrad_reduce<<<blocks, 256, 0, st>>>(partial, slices, q.I, g.Cs, g.Cb, dw);
+  AE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ae

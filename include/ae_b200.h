@@ -36,8 +36,8 @@ typedef void* ae_stream_t; /* cudaStream_t */
 
 /* arithmetic mode of the GEMM-shaped kernels */
 enum {
-  AE_PREC_FP32 = 0, /* fp32 storage; tcgen05 with 2-term bf16 operand split (3 MMAs), fp32 accumulate: rel <= 1e-4 */
-  AE_PREC_BF16 = 1  /* fp32 storage, operands rounded to bf16, fp32 accumulate: rel <= 1e-2 */
+  AE_PREC_FP32 = 0, /* operands as 2-term bf16 split (hi + lo planes), 3 tcgen05 MMAs per k-step, fp32 accumulate: rel <= 1e-4 */
+  AE_PREC_BF16 = 1  /* operands rounded to bf16 (one plane), fp32 accumulate: rel <= 1e-2 */
 };
 enum {
   AE_BACKEND_TC = 0,  /* tcgen05 / TMEM kernels */
@@ -49,7 +49,8 @@ enum {
   AE_OP_RAW = 0,        /* value = src */
   AE_OP_BNRELU = 1,     /* value = relu(src * scale[c] + shift[c])                (BatchNorm + ReLU forward) */
   AE_OP_BNBWD = 2,      /* value = A[c] * src + B[c] * (src2 - mean[c]) + C[c]    (BatchNorm backward apply) */
-  AE_OP_SIGMOID_BWD = 3 /* value = up * s * (1 - s), s = src2 (sigmoid output): up = src, or scalar * (s - src) when fused MSE */
+  AE_OP_SIGMOID_BWD = 3, /* value = up * s * (1 - s), s = src2 (sigmoid output): up = src, or scalar * (s - src) when fused MSE */
+  AE_OP_SPLIT_BF16 = 4   /* src = split-bf16 planes written by ae_split_operand (the only operand form the tcgen05 GEMMs take) */
 };
 
 /* per-BatchNorm-layer coefficient block: 8 rows of C floats */
@@ -102,6 +103,16 @@ int ae_device_supported(int ordinal);
 size_t ae_packed_weight_bytes(int cs, int cb, int precision, int backend);
 int ae_pack_conv_weight(const float* w, int cs, int cb, void* packed_fwd, void* packed_dgrad,
                         int precision, int backend, ae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ae_split_operand -- materialise an activation operand for the tcgen05 GEMMs (AE_BACKEND_TC).
+ *   Reads `count` fp32 NHWC values (channel = index % channels), applies the operand transform (RAW, BNRELU = the
+ *   BatchNorm2d + ReLU of NB:505-517 / NB:617-625, BNBWD = their backward) and writes split-bf16 planes
+ *   [nsplit][count] bf16: plane 0 = rn_bf16(v), plane 1 (AE_PREC_FP32 only) = rn_bf16(v - plane 0).
+ *   The GEMM kernels load these planes with TMA; pass them as an operand with mode AE_OP_SPLIT_BF16.
+ * ---------------------------------------------------------------------------------------- */
+size_t ae_split_operand_bytes(int64_t count, int precision);
+int ae_split_operand(const ae_operand_t* op, int channels, int64_t count, void* planes, int precision, ae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * ae_conv2d_s2_fwd -- big -> small 3x3 stride-2 pad-1 gather GEMM.

@@ -61,6 +61,18 @@ def operand(src, src2=None, bnc=None, scalar=0.0, mode=_lib.OP_RAW):
     return _lib.Operand(p(src), p(src2), p(bnc), float(scalar), int(mode))
 
 
+def conv_operand(backend, prec, channels, src, src2=None, bnc=None, mode=_lib.OP_RAW):
+    """Activation operand of a conv GEMM.  CUDA-core backend: the fp32 tensor + transform.  tcgen05 backend: the
+    split-bf16 planes ae_split_operand makes of it (returned second so the caller keeps them alive)."""
+    op = operand(src, src2, bnc, 0.0, mode)
+    if backend != "tc":
+        return op, None
+    count = src.numel()
+    planes = torch.empty(lib().ae_split_operand_bytes(count, PREC[prec]), dtype=torch.uint8, device=src.device)
+    _lib.check(lib().ae_split_operand(C.byref(op), channels, count, p(planes), PREC[prec], stream()))
+    return _lib.Operand(p(planes), None, None, 0.0, _lib.OP_SPLIT_BF16), planes
+
+
 def epilogue(mode=_lib.EPI_STORE, bias=None, y=None, bnc=None, stats=None):
     return _lib.Epilogue(int(mode), p(bias), p(y), p(bnc), p(stats))
 

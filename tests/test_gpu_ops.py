@@ -53,7 +53,7 @@ def test_conv_fwd(shape, mode, prec, backend):
     out = torch.empty(b, hs, hs, cs, device=d)
     stats = torch.zeros(2 * cs, dtype=torch.float64, device=d)
     g = _geom(b, hs, cb, cs)
-    op = gu.operand(xb, xb2, bncd, 0.0, mode)
+    op, _keep = gu.conv_operand(backend, prec, cb, xb, xb2, bncd, mode)
     ep = gu.epilogue(_lib.EPI_BIAS_STATS, biasd, None, None, stats)
     _lib.check(gu.lib().ae_conv2d_s2_fwd(C.byref(g), C.byref(op), gu.p(pf), C.byref(ep), gu.p(out), gu.PREC[prec],
                                         gu.BACK[backend], gu.stream()))
@@ -95,7 +95,7 @@ def test_conv_dgrad_is_transposed_conv(shape, mode, prec, backend):
     _, pd = gu.pack_conv(wd, cs, cb, prec, backend)
     g = _geom(b, hs, cb, cs)
     sd, sd2, bncd = gu.nhwc(small).to(d), gu.nhwc(small2).to(d), bnc.to(d)   # keep alive: operand holds raw pointers
-    op = gu.operand(sd, sd2, bncd, 0.0, mode)
+    op, _keep = gu.conv_operand(backend, prec, cs, sd, sd2, bncd, mode)
     out = torch.empty(b, 2 * hs, 2 * hs, cb, device=d)
     stats = torch.zeros(2 * cb, dtype=torch.float64, device=d)
     biasd = bias.to(d)
@@ -141,8 +141,8 @@ def test_conv_wgrad(shape, prec, backend):
     part = torch.empty(nbytes + 16, dtype=torch.uint8, device=d)
     dw = torch.full((cs, cb, 3, 3), float("nan"), device=d)
     bigd, bncbd, dzd, yd, bncsd = gu.nhwc(big).to(d), bnc_b.to(d), gu.nhwc(dz).to(d), gu.nhwc(y).to(d), bnc_s.to(d)
-    opb = gu.operand(bigd, None, bncbd, 0.0, _lib.OP_BNRELU)
-    ops = gu.operand(dzd, yd, bncsd, 0.0, _lib.OP_BNBWD)
+    opb, _k1 = gu.conv_operand(backend, prec, cb, bigd, None, bncbd, _lib.OP_BNRELU)
+    ops, _k2 = gu.conv_operand(backend, prec, cs, dzd, yd, bncsd, _lib.OP_BNBWD)
     _lib.check(gu.lib().ae_conv2d_s2_wgrad(C.byref(g), C.byref(opb), C.byref(ops), gu.p(dw), gu.p(part), nbytes,
                                           gu.PREC[prec], gu.BACK[backend], gu.stream()))
     torch.cuda.synchronize()
