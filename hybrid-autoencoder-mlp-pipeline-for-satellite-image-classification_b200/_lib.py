@@ -59,6 +59,8 @@ _SIGS = {
     "ae_thin_scatter_sigmoid_fwd": (c_int, [P(Operand), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ae_thin_wgrad": (c_int, [P(Operand), P(Operand), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "ae_thin_wgrad_workspace_bytes": (c_size_t, [c_int]),
+    "ae_thin_bwd_fused": (c_int, [P(Operand), P(Operand), c_void_p, P(Epilogue), c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_int, c_void_p]),
     "ae_bn_finalize": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ae_bn_bwd_reduce": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ae_linear_fwd": (c_int, [P(Operand), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -22,6 +22,8 @@ int thin_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* b
 int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes,
                int batch, cudaStream_t st);
 size_t thin_wgrad_workspace_bytes(int batch);
+int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
+                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st);
 int bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float* rmean, float* rvar,
                 float* bnc, int C, int training, cudaStream_t st);
 int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta, int C,
@@ -158,6 +160,14 @@ int ae_thin_wgrad(const ae_operand_t* wide, const ae_operand_t* thin, float* dw,
   AE_CHECK(wide && thin && dw && partials && batch >= 1, "ae_thin_wgrad: bad argument");
   return thin_wgrad(make_operand(wide, 32), make_operand(thin, 3), dw, dbias_thin, partials, partials_bytes, batch,
                     (cudaStream_t)stream);
+}
+
+int ae_thin_bwd_fused(const ae_operand_t* wide, const ae_operand_t* thin, const float* w, const ae_epilogue_t* epi,
+                      float* out_wide, float* dw, float* dbias_thin, void* partials, size_t partials_bytes, int batch,
+                      ae_stream_t stream) {
+  AE_CHECK(wide && thin && w && epi && out_wide && dw && partials && batch >= 1, "ae_thin_bwd_fused: bad argument");
+  return thin_bwd_fused(make_operand(wide, 32), make_operand(thin, 3), w, make_epilogue(epi, 32), out_wide, dw, dbias_thin,
+                        partials, partials_bytes, batch, (cudaStream_t)stream);
 }
 
 int ae_bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float* running_mean,

@@ -14,6 +14,8 @@ int thin_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* b
 int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes,
                int batch, cudaStream_t st);
 size_t thin_wgrad_workspace_bytes(int batch);
+int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
+                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st);
 int bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float* rmean, float* rvar,
                 float* bnc, int C, int training, cudaStream_t st);
 int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta, int C,
@@ -23,6 +25,11 @@ int softmax_ce(const float* logits, const int64_t* labels, int B, int C, float g
 int adam_step_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                    float wd, float gscale, int* step_dev, cudaStream_t st);
 int head_out(const float* hid_pre, const float* w2, const float* b2, float* logits, int B, int H, int C, cudaStream_t st);
+size_t head_fused_workspace_floats(int B, int L, int C);
+int head_fused_step(const float* z, const int64_t* labels, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* logits, float* dz, float* gw1, float* gb1, float* gw2, float* gb2,
+                    float* loss, const double* sse, double numel, float alpha, float* partial, unsigned int* counter,
+                    int B, int L, int C, cudaStream_t st);
 int head_backward_small(const float* dlogits, const float* w2, const float* hid_pre, float* dhid, float* dw2, float* db2,
                         int B, int H, int C, cudaStream_t st);
 
@@ -99,6 +106,7 @@ struct ae_engine {
   float* partial = nullptr;
   size_t partial_bytes = 0;
   double* sse = nullptr;
+  unsigned int* head_counter = nullptr;
   double* stats_base = nullptr;
   size_t stats_bytes = 0;
   int fc_split = 16;
@@ -250,8 +258,10 @@ static size_t carve(ae_engine* e, char* base) {
   upd((size_t)colgemm_default_split((int)B, 128, L) * 128 * L * 4);
   upd((size_t)e->fc_split * B * L * 4);
   upd(thin_wgrad_workspace_bytes((int)B));
+  upd(head_fused_workspace_floats((int)B, L, NC) * 4);
   e->partial_bytes = pb;
   e->partial = (float*)take(pb);
+  e->head_counter = (unsigned int*)take(256);
   return off + 256;
 }
 
@@ -350,6 +360,7 @@ int ae_engine_bind_workspace(ae_engine_t* e, void* workspace, size_t bytes) {
   AE_CHECK(((uintptr_t)workspace & 255) == 0, "ae_engine_bind_workspace: workspace must be 256-byte aligned");
   e->ws = workspace; e->ws_bytes = bytes;
   carve(e, static_cast<char*>(workspace));
+  AE_CUDA(cudaMemset(e->head_counter, 0, 256));
   return 0;
 }
 
@@ -550,8 +561,9 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
   Part& P = e->part[AE_PART_DEC];
   const int L = e->L;
   // convT4 (32 -> 3)
-  AE_TRY(thin_wgrad(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), thin_up, P.G(14), P.G(15), e->partial, e->partial_bytes, batch, st));
-  AE_TRY(thin_gather_fwd(thin_up, P.P(14), relubwd_epilogue(e->t[2], P.bn[2].bnc, P.bn[2].stats_b, 32), e->dzt[2], batch, st));
+  AE_TRY(thin_bwd_fused(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), thin_up, P.P(14),
+                        relubwd_epilogue(e->t[2], P.bn[2].bnc, P.bn[2].stats_b, 32), e->dzt[2], P.G(14), P.G(15), e->partial,
+                        e->partial_bytes, batch, st));
   AE_TRY(bn_bwd_reduce(P.bn[2].stats_b, (int64_t)batch * 1024, P.P(P.bn[2].gamma), P.bn[2].bnc, P.G(P.bn[2].gamma),
                        P.G(P.bn[2].beta), 32, st));
   for (int i = 2; i >= 0; --i) {
@@ -650,10 +662,13 @@ int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int bat
   AE_CHECK(e && x && labels && loss_out, "ae_train_step: null argument");
   AE_TRY(ae_encoder_forward(e, x, batch, 1, nullptr, stream));
   AE_TRY(decoder_forward_impl(e, e->z, batch, 1, nullptr, x, st));
-  AE_TRY(ae_head_forward(e, e->z, batch, nullptr, stream));
   const double numel = (double)batch * 12288.0;
-  AE_TRY(softmax_ce(e->logits, labels, batch, e->NC, 1.f, loss_out, e->dlogits, nullptr, e->sse, numel, alpha, st));
-  AE_TRY(ae_head_backward(e, e->dlogits, batch, e->dz_head, stream));
+  {  // classifier head: forward + cross-entropy + backward + loss assembly in one launch
+    AE_TRY(check_part(e, AE_PART_HEAD, true));
+    Part& H = e->part[AE_PART_HEAD];
+    AE_TRY(head_fused_step(e->z, labels, H.P(0), H.P(1), H.P(2), H.P(3), e->logits, e->dz_head, H.G(0), H.G(1), H.G(2),
+                           H.G(3), loss_out, e->sse, numel, alpha, e->partial, e->head_counter, batch, e->L, e->NC, st));
+  }
   Operand up;
   up.src = x; up.src2 = e->xhat; up.bnc = nullptr; up.scalar = (float)(2.0 * (double)alpha / numel);
   up.mode = AE_OP_SIGMOID_BWD; up.C = 1;

@@ -2,18 +2,28 @@
 // (NB:628-629).  K=27 / N=3 do not fill a tensor-core tile; these are bandwidth kernels on CUDA cores.
 //   thin = [B,3,64,64] NCHW fp32 (the reference's image layout), wide = [B,32,32,32] NHWC fp32.
 //   both layers store their weight as [32][3][3][3] = [c32][c3][ky][kx].
-#include "common.cuh"
+//
+// All kernels are persistent and work on tiles of 4 wide rows x 32 wide columns (128 wide pixels = 8 thin rows) of
+// one image.  The raw thin rows and the raw wide tile of the NEXT tile are fetched by TMA bulk copies
+// (cp.async.bulk + mbarrier, double buffered) while the current tile is computed; one in-place pass applies the
+// operand transform once per element; 128 threads, one wide pixel per thread.
+#include "tc_common.cuh"
 
 namespace ae {
 
 static constexpr int TH = 64, TW = 64, WH = 32, WW = 32, WC = 32;
+static constexpr int TT_THREADS = 128;
+static constexpr int TILE_ROWS = 4;                    // wide rows per tile
+static constexpr int TILES_PER_IMAGE = WH / TILE_ROWS; // 8
+static constexpr int XS_ROWS = 2 * TILE_ROWS + 1;      // thin rows 8*tr-1 .. 8*tr+7
+static constexpr int XS_PITCH = 72;                    // thin column c at index c + 4; index 3 = left zero padding
+static constexpr int XS_FLOATS = 3 * XS_ROWS * XS_PITCH;
+static constexpr int TW_PART = 868;                    // 864 weights + 3 thin-bias sums + 1 pad
 
-__device__ __forceinline__ float thin_value(const Operand& op, size_t idx) {
-  const float a = __ldg(op.src + idx);
+__device__ __forceinline__ float thin_transform(const Operand& op, float a, float s) {
   if (op.mode == AE_OP_RAW) return a;
-  const float s = __ldg(op.src2 + idx);                       // AE_OP_SIGMOID_BWD
-  const float up = (op.scalar != 0.f) ? op.scalar * (s - a) : a;  // fused MSE gradient, or a given upstream gradient
-  return up * s * (1.f - s);
+  const float up = (op.scalar != 0.f) ? op.scalar * (s - a) : a;   // fused MSE gradient, or a given upstream gradient
+  return up * s * (1.f - s);                                       // AE_OP_SIGMOID_BWD
 }
 
 // lane l ends with the sum over the warp's 32 lanes of element v[l]  (31 shuffles)
@@ -31,282 +41,500 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+static constexpr int XS_BYTES = XS_FLOATS * 4;
+static constexpr int WT_FLOATS = 128 * 32;             // one wide tile
+static constexpr int WT_BYTES = WT_FLOATS * 4;
+
+// shared-memory layout of one k_thin stage (floats): [xs][xs2 if the thin operand has two sources][wide][wide2 if BNBWD]
+struct ThinStage {
+  int xs2, wide, wide2, floats;
+};
+__host__ __device__ inline ThinStage thin_stage_layout(int thin_mode, int wide_mode, bool wgrad) {
+  ThinStage L;
+  int off = XS_FLOATS;
+  L.xs2 = off; if (thin_mode != AE_OP_RAW) off += XS_FLOATS;
+  L.wide = off; if (wgrad) off += WT_FLOATS;
+  L.wide2 = off; if (wgrad && wide_mode == AE_OP_BNBWD) off += WT_FLOATS;
+  L.floats = off;
+  return L;
+}
+
 // ---------------------------------------------------------------------------------------------
-// thin -> wide gather (conv1 forward; convT4 data gradient).  One thread per wide pixel.
+// k_thin: thin -> wide gather (conv1 forward; convT4 data gradient) and / or the weight gradient of a thin layer
+//   GATHER: out[p][c32] = epilogue(sum_k patch(p,k) * w[c32][k]), k = (c3,ky,kx); per-channel statistics
+//   WGRAD : partial[cta][c32][k] = sum_p wide(p,c32) * patch(p,k); partial[cta][864+c3] = sum of the thin operand
+// Both read the same staged thin rows, so the fused convT4 backward touches x / x_hat once.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_thin_gather(Operand thin, const float* __restrict__ w, Epilogue e,
-                                                     float* __restrict__ out, int batch) {
-  __shared__ __align__(16) float Wsm[27][32];
+template <bool GATHER, bool WGRAD>
+__global__ void __launch_bounds__(TT_THREADS) k_thin(Operand thin, Operand wide, const float* __restrict__ w, Epilogue e,
+                                                     float* __restrict__ out, float* __restrict__ partial, int batch) {
+  extern __shared__ __align__(128) float smem_f[];
+  const ThinStage L = thin_stage_layout(thin.mode, wide.mode, WGRAD);
+  float* stage0 = smem_f;                               // two stages of L.floats floats
+  float* Wsm = smem_f + 2 * L.floats;                   // [27][32]                 (GATHER)
+  float* sbn = Wsm + 27 * 32;                           // [4][32] scale/shift/mean/rstd (GATHER, RELUBWD)
+  float* wbn = sbn + 4 * 32;                            // [4][32] coefficients of the wide operand (WGRAD)
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ float sStat[2][32];
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < 27 * 32; i += 128) {
-    const int c32 = i / 27, k = i - c32 * 27;
-    Wsm[k][c32] = __ldg(w + i);
+  __shared__ float sB[TT_THREADS / 32][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+
+  if (tid == 0) {
+    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
   }
-  if (tid < 32) { sStat[0][tid] = 0.f; sStat[1][tid] = 0.f; }
+  if (GATHER) {
+    for (int i = tid; i < 27 * 32; i += TT_THREADS) {
+      const int c32 = i / 27, k = i - c32 * 27;
+      Wsm[k * 32 + c32] = __ldg(w + i);
+    }
+    if (e.mode == AE_EPI_RELUBWD_STATS) {
+      const int rows[4] = {AE_BNC_SCALE, AE_BNC_SHIFT, AE_BNC_MEAN, AE_BNC_RSTD};
+      sbn[tid] = __ldg(e.bnc + rows[tid >> 5] * WC + lane);
+    }
+    if (tid < 32) { sStat[0][tid] = 0.f; sStat[1][tid] = 0.f; }
+  }
+  if (WGRAD && wide.mode != AE_OP_RAW) {
+    // BNRELU: scale, shift;  BNBWD: A, B, C, mean
+    const int rows_relu[4] = {AE_BNC_SCALE, AE_BNC_SHIFT, AE_BNC_SCALE, AE_BNC_SHIFT};
+    const int rows_bwd[4] = {AE_BNC_A, AE_BNC_B, AE_BNC_C, AE_BNC_MEAN};
+    wbn[tid] = __ldg(wide.bnc + (wide.mode == AE_OP_BNRELU ? rows_relu[tid >> 5] : rows_bwd[tid >> 5]) * WC + lane);
+  }
+  for (int i = tid; i < 2 * 3 * XS_ROWS; i += TT_THREADS) {   // left zero padding of both stages, never overwritten
+    const int st = i / (3 * XS_ROWS), r = i - st * 3 * XS_ROWS;
+    stage0[st * L.floats + r * XS_PITCH + 3] = 0.f;
+  }
+  float st1 = 0.f, st2 = 0.f;                             // GATHER: lane-owned channel statistics
+  float bsum[3] = {0.f, 0.f, 0.f};                        // WGRAD: thin-operand sums
+  // WGRAD register tile: channels c4*4..+3 x patch taps kg*7..+6 (tap 27 is padding)
+  const int c4 = lane & 7, kg = lane >> 3;
+  int koff[7];
+  float wacc[4][7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    int k = kg * 7 + j;
+    if (k > 26) k = 26;
+    const int c3 = k / 9, rr = k - c3 * 9, ky = rr / 3, kx = rr - ky * 3;
+    koff[j] = (c3 * XS_ROWS + ky) * XS_PITCH + 3 + kx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wacc[i][j] = 0.f;
+  }
   __syncthreads();
 
-  const int m = blockIdx.x * 128 + tid;  // grid covers batch*1024 exactly
-  const int ox = m & 31, oy = (m >> 5) & 31, n = m >> 10;
-  float acc[32];
+  const int tiles = batch * TILES_PER_IMAGE;
+  // one thread: fetch the raw data of `tile` into stage st
+  auto issue = [&](int tile, int st) {
+    const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;
+    const uint32_t bar = bar0 + 8u * st;
+    float* base = stage0 + st * L.floats;
+    const int r_first = tr == 0 ? 1 : 0;                    // thin row -1 does not exist: zero-filled by the transform pass
+    const int nsrc = thin.mode != AE_OP_RAW ? 2 : 1;
+    uint32_t bytes = (uint32_t)(3 * (XS_ROWS - r_first) * TW * 4 * nsrc);
+    if (WGRAD) bytes += WT_BYTES * (wide.mode == AE_OP_BNBWD ? 2 : 1);
+    mbar_arrive_expect_tx(bar, bytes);
+    for (int c3 = 0; c3 < 3; ++c3)
+      for (int r = r_first; r < XS_ROWS; ++r) {
+        const size_t off = (((size_t)n * 3 + c3) * TH + (2 * TILE_ROWS * tr - 1 + r)) * TW;
+        const int so = (c3 * XS_ROWS + r) * XS_PITCH + 4;
+        bulk_copy_g2s(smem_u32(base + so), thin.src + off, TW * 4, bar);
+        if (nsrc == 2) bulk_copy_g2s(smem_u32(base + L.xs2 + so), thin.src2 + off, TW * 4, bar);
+      }
+    if (WGRAD) {
+      const size_t m0 = ((size_t)n * WH + tr * TILE_ROWS) * WW;
+      bulk_copy_g2s(smem_u32(base + L.wide), wide.src + m0 * WC, WT_BYTES, bar);
+      if (wide.mode == AE_OP_BNBWD) bulk_copy_g2s(smem_u32(base + L.wide2), wide.src2 + m0 * WC, WT_BYTES, bar);
+    }
+  };
+
+  if (tid == 0 && (int)blockIdx.x < tiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int st = it & 1;
+    const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;
+    const size_t m0 = ((size_t)n * WH + tr * TILE_ROWS) * WW;      // first wide pixel of the tile
+    float* xs = stage0 + st * L.floats;
+    float* as = xs + L.wide;
+    if (tid == 0 && tile + (int)gridDim.x < tiles) {
+      fence_proxy_async();                                // the other stage was last touched by generic-proxy accesses
+      issue(tile + gridDim.x, st ^ 1);
+    }
+    float4 y4[8];                                         // RELUBWD: raw output row of this thread's pixel (prefetched)
+    const size_t row = (m0 + (size_t)warp * WW + lane) * WC;
+    if (GATHER && e.mode == AE_EPI_RELUBWD_STATS) {
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+      for (int q4 = 0; q4 < 8; ++q4) y4[q4] = __ldg(reinterpret_cast<const float4*>(e.y + row) + q4);
+    }
+    mbar_wait(bar0 + 8u * st, (it >> 1) & 1);
+    // ---- transform pass (in place, once per element) ----
+    if (thin.mode != AE_OP_RAW || tr == 0 || WGRAD) {
+      for (int i = tid; i < 3 * XS_ROWS * 16; i += TT_THREADS) {
+        const int q = i & 15, r = (i >> 4) % XS_ROWS, c3 = i / (16 * XS_ROWS);
+        float* px = xs + (c3 * XS_ROWS + r) * XS_PITCH + 4 + q * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r > 0 || tr > 0) {
+          v = *reinterpret_cast<const float4*>(px);
+          if (thin.mode != AE_OP_RAW) {
+            const float4 sg = *reinterpret_cast<const float4*>(px + L.xs2);
+            v.x = thin_transform(thin, v.x, sg.x); v.y = thin_transform(thin, v.y, sg.y);
+            v.z = thin_transform(thin, v.z, sg.z); v.w = thin_transform(thin, v.w, sg.w);
+          }
+          if (WGRAD && r >= 1) bsum[c3 == 0 ? 0 : (c3 == 1 ? 1 : 2)] += (v.x + v.y) + (v.z + v.w);
+        }
+        if (thin.mode != AE_OP_RAW || (r == 0 && tr == 0)) *reinterpret_cast<float4*>(px) = v;
+      }
+    }
+    if (WGRAD && wide.mode != AE_OP_RAW) {
 #pragma unroll
-  for (int c3 = 0; c3 < 3; ++c3) {
+      for (int j = 0; j < 8; ++j) {
+        const int i = tid + j * TT_THREADS;               // float4 index; channel chunk = i & 7
+        const int c = (i & 7) * 4;
+        float4 v = *reinterpret_cast<const float4*>(as + i * 4);
+        const float4 k0 = *reinterpret_cast<const float4*>(wbn + c), k1 = *reinterpret_cast<const float4*>(wbn + 32 + c);
+        if (wide.mode == AE_OP_BNRELU) {
+          v.x = fmaxf(fmaf(v.x, k0.x, k1.x), 0.f); v.y = fmaxf(fmaf(v.y, k0.y, k1.y), 0.f);
+          v.z = fmaxf(fmaf(v.z, k0.z, k1.z), 0.f); v.w = fmaxf(fmaf(v.w, k0.w, k1.w), 0.f);
+        } else {                                          // dy = A*dz + B*(y - mean) + C   (same order as load_operand4)
+          const float4 y = *reinterpret_cast<const float4*>(xs + L.wide2 + i * 4);
+          const float4 k2 = *reinterpret_cast<const float4*>(wbn + 64 + c), k3 = *reinterpret_cast<const float4*>(wbn + 96 + c);
+          v.x = fmaf(k0.x, v.x, fmaf(k1.x, y.x - k3.x, k2.x)); v.y = fmaf(k0.y, v.y, fmaf(k1.y, y.y - k3.y, k2.y));
+          v.z = fmaf(k0.z, v.z, fmaf(k1.z, y.z - k3.z, k2.z)); v.w = fmaf(k0.w, v.w, fmaf(k1.w, y.w - k3.w, k2.w));
+        }
+        *reinterpret_cast<float4*>(as + i * 4) = v;
+      }
+    }
+    __syncthreads();
+
+    if (GATHER) {
+      const int x = lane, r = warp;                     // wide pixel (r, x) of the tile
+      float acc[32];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = 2 * oy - 1 + ky;
+      for (int c = 0; c < 32; ++c) acc[c] = 0.f;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox - 1 + kx;
-        float v = 0.f;
-        if (iy >= 0 && ix >= 0) v = thin_value(thin, (((size_t)n * 3 + c3) * TH + iy) * TW + ix);
-        const int k = c3 * 9 + ky * 3 + kx;
+      for (int c3 = 0; c3 < 3; ++c3) {
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 wv = *reinterpret_cast<const float4*>(&Wsm[k][c4 * 4]);
-          acc[c4 * 4 + 0] = fmaf(v, wv.x, acc[c4 * 4 + 0]);
-          acc[c4 * 4 + 1] = fmaf(v, wv.y, acc[c4 * 4 + 1]);
-          acc[c4 * 4 + 2] = fmaf(v, wv.z, acc[c4 * 4 + 2]);
-          acc[c4 * 4 + 3] = fmaf(v, wv.w, acc[c4 * 4 + 3]);
+        for (int ky = 0; ky < 3; ++ky) {
+          const float* ra = xs + (c3 * XS_ROWS + 2 * r + ky) * XS_PITCH + 3 + 2 * x;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float xa = ra[kx];
+            const float* wk = Wsm + (c3 * 9 + ky * 3 + kx) * 32;
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 wv = *reinterpret_cast<const float4*>(wk + q4 * 4);
+              acc[q4 * 4 + 0] = fmaf(xa, wv.x, acc[q4 * 4 + 0]);
+              acc[q4 * 4 + 1] = fmaf(xa, wv.y, acc[q4 * 4 + 1]);
+              acc[q4 * 4 + 2] = fmaf(xa, wv.z, acc[q4 * 4 + 2]);
+              acc[q4 * 4 + 3] = fmaf(xa, wv.w, acc[q4 * 4 + 3]);
+            }
+          }
+        }
+      }
+      float s2v[32];
+      if (e.mode == AE_EPI_RELUBWD_STATS) {
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float yv[4] = {y4[q4].x, y4[q4].y, y4[q4].z, y4[q4].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = q4 * 4 + j;
+            const float z = fmaf(yv[j], sbn[c], sbn[32 + c]);
+            const float d = z > 0.f ? acc[c] : 0.f;
+            acc[c] = d;
+            s2v[c] = d * ((yv[j] - sbn[64 + c]) * sbn[96 + c]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float d = acc[c] + (e.bias ? __ldg(e.bias + c) : 0.f);
+          acc[c] = d;
+          s2v[c] = d * d;
+        }
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4)
+        reinterpret_cast<float4*>(out + row)[q4] = make_float4(acc[q4 * 4], acc[q4 * 4 + 1], acc[q4 * 4 + 2], acc[q4 * 4 + 3]);
+      if (e.mode != AE_EPI_STORE && e.stats) {
+        st1 += warp_colsum32(acc, lane);
+        st2 += warp_colsum32(s2v, lane);
+      }
+    }
+
+    if (WGRAD) {
+      // warp q accumulates over wide pixels q*32 .. q*32+31 of the tile (= wide row q)
+      const float* arow = as + warp * 32 * 32 + c4 * 4;
+      const float* prow = xs + 2 * warp * XS_PITCH;
+#pragma unroll 4
+      for (int pc = 0; pc < 32; ++pc) {
+        const float4 a4 = *reinterpret_cast<const float4*>(arow + pc * 32);
+        const float* pb = prow + 2 * pc;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const float t = pb[koff[j]];
+          wacc[0][j] = fmaf(a4.x, t, wacc[0][j]);
+          wacc[1][j] = fmaf(a4.y, t, wacc[1][j]);
+          wacc[2][j] = fmaf(a4.z, t, wacc[2][j]);
+          wacc[3][j] = fmaf(a4.w, t, wacc[3][j]);
         }
       }
     }
+    __syncthreads();                                      // every warp is done with stage st before it is refilled
   }
-  const size_t row = (size_t)m * WC;
-  float s2v[32];
-  if (e.mode == AE_EPI_RELUBWD_STATS) {
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 y4 = __ldg(reinterpret_cast<const float4*>(e.y + row) + c4);
-      const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = c4 * 4 + j;
-        const float z = fmaf(yv[j], __ldg(e.bnc + AE_BNC_SCALE * WC + c), __ldg(e.bnc + AE_BNC_SHIFT * WC + c));
-        acc[c] = z > 0.f ? acc[c] : 0.f;
-        s2v[c] = acc[c] * ((yv[j] - __ldg(e.bnc + AE_BNC_MEAN * WC + c)) * __ldg(e.bnc + AE_BNC_RSTD * WC + c));
-      }
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      if (e.bias) acc[c] += __ldg(e.bias + c);
-      s2v[c] = acc[c] * acc[c];
-    }
-  }
-#pragma unroll
-  for (int c4 = 0; c4 < 8; ++c4)
-    reinterpret_cast<float4*>(out + row)[c4] = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
-  if (e.mode != AE_EPI_STORE && e.stats) {
-    const float a = warp_colsum32(acc, lane);
-    const float b = warp_colsum32(s2v, lane);
-    atomicAdd(&sStat[0][lane], a);
-    atomicAdd(&sStat[1][lane], b);
+
+  if (GATHER && e.mode != AE_EPI_STORE && e.stats) {
+    atomicAdd(&sStat[0][lane], st1);
+    atomicAdd(&sStat[1][lane], st2);
     __syncthreads();
     if (tid < 32) {
       atomicAdd(e.stats + tid, (double)sStat[0][tid]);
       atomicAdd(e.stats + WC + tid, (double)sStat[1][tid]);
     }
   }
+  if (WGRAD) {
+    float* red = stage0 + L.wide;                       // [4 warps][32 ch][28] (stage 0's wide tile: nothing in flight any more)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 7; ++j) red[(warp * 32 + c4 * 4 + i) * 28 + kg * 7 + j] = wacc[i][j];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float sm = warp_sum(bsum[c]);
+      if (lane == 0) sB[warp][c] = sm;
+    }
+    __syncthreads();
+    float* dst = partial + (size_t)blockIdx.x * TW_PART;
+    for (int i = tid; i < 864; i += TT_THREADS) {
+      const int c = i / 27, k = i - c * 27;
+      const int o = c * 28 + k;
+      dst[i] = (red[o] + red[32 * 28 + o]) + (red[2 * 32 * 28 + o] + red[3 * 32 * 28 + o]);
+    }
+    if (tid < 3) dst[864 + tid] = (sB[0][tid] + sB[1][tid]) + (sB[2][tid] + sB[3][tid]);
+    if (tid == 3) dst[867] = 0.f;
+  }
+}
+
+// Fixed-order two-level reduction of the per-CTA partials: block b owns 32 outputs, its 32 warps each sum a
+// contiguous share of the partials, then one warp adds the 32 shares (deterministic).
+__global__ void __launch_bounds__(1024) k_thin_wgrad_reduce(const float* __restrict__ partial, int nparts,
+                                                            float* __restrict__ dw, float* __restrict__ dbias) {
+  __shared__ float red[32][33];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int per = (nparts + 31) / 32;
+  const int p0 = wq * per, p1 = min(nparts, p0 + per);
+  float sm = 0.f;
+  if (i < 867) {
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {
+      const float v0 = __ldg(partial + (size_t)p * TW_PART + i), v1 = __ldg(partial + (size_t)(p + 1) * TW_PART + i);
+      const float v2 = __ldg(partial + (size_t)(p + 2) * TW_PART + i), v3 = __ldg(partial + (size_t)(p + 3) * TW_PART + i);
+      sm += (v0 + v1) + (v2 + v3);
+    }
+    for (; p < p1; ++p) sm += __ldg(partial + (size_t)p * TW_PART + i);
+  }
+  red[wq][lane] = sm;
+  __syncthreads();
+  if (wq == 0 && i < 867) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][lane];
+    if (i < 864) dw[i] = t;
+    else if (dbias) dbias[i - 864] = t;
+  }
+}
+
+static int thin_blocks(int batch) {
+  const int tiles = batch * TILES_PER_IMAGE;
+  return tiles < 4 * 148 ? tiles : 4 * 148;
+}
+size_t thin_wgrad_workspace_bytes(int batch) { return (size_t)thin_blocks(batch) * TW_PART * sizeof(float); }
+
+template <bool GATHER, bool WGRAD>
+static int launch_thin(const Operand& thin, const Operand& wide, const float* w, const Epilogue& e, float* out,
+                       float* partial, int batch, cudaStream_t st) {
+  const ThinStage L = thin_stage_layout(thin.mode, wide.mode, WGRAD);
+  const size_t smem = sizeof(float) * (2 * (size_t)L.floats + 27 * 32 + 8 * 32);
+  static bool attr_done = false;
+  if (!attr_done) {
+    // the largest layout (two-source thin operand, BatchNorm-backward wide operand)
+    const ThinStage Lmax = thin_stage_layout(AE_OP_SIGMOID_BWD, AE_OP_BNBWD, WGRAD);
+    AE_CUDA(cudaFuncSetAttribute(k_thin<GATHER, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(float) * (2 * (size_t)Lmax.floats + 27 * 32 + 8 * 32))));
+    attr_done = true;
+  }
+  k_thin<GATHER, WGRAD><<<thin_blocks(batch), TT_THREADS, smem, st>>>(thin, wide, w, e, out, partial, batch);
+  AE_LAUNCH_CHECK();
+  return 0;
+}
+
+static int check_wide_operand(const Operand& wide) {
+  AE_CHECK(wide.mode == AE_OP_RAW || wide.mode == AE_OP_BNRELU || wide.mode == AE_OP_BNBWD, "wide operand: mode %d not supported", wide.mode);
+  AE_CHECK(((uintptr_t)wide.src & 15) == 0 && (wide.mode != AE_OP_BNBWD || ((uintptr_t)wide.src2 & 15) == 0),
+           "wide operand: tensors must be 16-byte aligned");
+  return 0;
+}
+
+static int check_thin_operand(const Operand& thin) {
+  AE_CHECK(thin.mode == AE_OP_RAW || thin.mode == AE_OP_SIGMOID_BWD, "thin operand: mode %d not supported", thin.mode);
+  AE_CHECK(((uintptr_t)thin.src & 15) == 0 && (thin.mode == AE_OP_RAW || ((uintptr_t)thin.src2 & 15) == 0),
+           "thin operand: image tensors must be 16-byte aligned");
+  return 0;
 }
 
 int thin_gather_fwd(const Operand& thin, const float* w, const Epilogue& epi, float* out, int batch, cudaStream_t st) {
-  k_thin_gather<<<batch * 8, 128, 0, st>>>(thin, w, epi, out, batch);
+  AE_TRY(check_thin_operand(thin));
+  return launch_thin<true, false>(thin, raw_operand(nullptr), w, epi, out, nullptr, batch, st);
+}
+
+int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes,
+               int batch, cudaStream_t st) {
+  AE_TRY(check_thin_operand(thin));
+  AE_TRY(check_wide_operand(wide));
+  const int blocks = thin_blocks(batch);
+  AE_CHECK(bytes >= (size_t)blocks * TW_PART * sizeof(float), "thin_wgrad: workspace too small");
+  AE_TRY((launch_thin<false, true>(thin, wide, nullptr, store_epilogue(), nullptr, static_cast<float*>(partials), batch, st)));
+  k_thin_wgrad_reduce<<<(867 + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(partials), blocks, dw, dbias);
+  AE_LAUNCH_CHECK();
+  return 0;
+}
+
+// Fused backward of the thin transposed convolution (NB:628): weight / bias gradient and the data gradient
+// (gather with the ReLU-backward epilogue) from one pass over the thin operand.
+int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
+                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st) {
+  AE_TRY(check_thin_operand(thin));
+  AE_TRY(check_wide_operand(wide));
+  const int blocks = thin_blocks(batch);
+  AE_CHECK(bytes >= (size_t)blocks * TW_PART * sizeof(float), "thin_bwd_fused: workspace too small");
+  AE_TRY((launch_thin<true, true>(thin, wide, w, epi, out_wide, static_cast<float*>(partials), batch, st)));
+  k_thin_wgrad_reduce<<<(867 + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(partials), blocks, dw, dbias);
   AE_LAUNCH_CHECK();
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// wide -> thin scatter + sigmoid (+ squared error): convT4 forward.  One thread per wide pixel,
-// producing the 2x2x3 output quad it alone owns (no atomics).
+// wide -> thin scatter + sigmoid (+ squared error): convT4 forward.  The transformed wide tile (9 rows x 33
+// columns with a zero halo) is staged once; every thread produces the 2x2x3 output quads of two vertically
+// adjacent wide pixels (no atomics on the output).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_thin_scatter_sigmoid(Operand wide, const float* __restrict__ w,
-                                                              const float* __restrict__ bias, float* __restrict__ x_hat,
-                                                              const float* __restrict__ x, double* __restrict__ sse,
-                                                              int batch) {
-  __shared__ __align__(16) float Wsm[9][3][32];  // [tap][co][ci]
-  __shared__ float red[4];
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < 27 * 32; i += 128) {
+static constexpr int AS_ROWS = TILE_ROWS + 1, AS_COLS = WW + 1;
+
+__global__ void __launch_bounds__(TT_THREADS) k_thin_scatter_sigmoid(Operand wide, const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, float* __restrict__ x_hat,
+                                                                     const float* __restrict__ x, double* __restrict__ sse,
+                                                                     int batch) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* as = smem_f;                                   // [AS_ROWS][AS_COLS][32], 16-byte chunk c of pixel p at c ^ (p & 7)
+  float* Wsm = as + AS_ROWS * AS_COLS * 32;             // [9 taps][3 co][32 ci]
+  __shared__ float red[TT_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 27 * 32; i += TT_THREADS) {
     const int ci = i / 27, r = i - ci * 27, co = r / 9, tap = r - co * 9;
-    Wsm[tap][co][ci] = __ldg(w + i);
+    Wsm[(tap * 3 + co) * 32 + ci] = __ldg(w + i);
   }
-  __syncthreads();
-  const int m = blockIdx.x * 128 + tid;
-  const int ix = m & 31, iy = (m >> 5) & 31, n = m >> 10;
-
-  float acc[2][2][3];
+  const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+  float err = 0.f;
+  const int tiles = batch * TILES_PER_IMAGE;
+  constexpr int UNITS = AS_ROWS * AS_COLS * 8;
+  constexpr int ITER = (UNITS + TT_THREADS - 1) / TT_THREADS;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;
+    __syncthreads();
+    {
+      float4 buf[ITER];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+      for (int j = 0; j < ITER; ++j) {
+        const int i = tid + j * TT_THREADS;
+        const int q = i & 7, p = i >> 3;
+        const int pr = p / AS_COLS, pc = p - pr * AS_COLS;
+        const int iy = tr * TILE_ROWS + pr;
+        const bool valid = i < UNITS && iy < WH && pc < WW;
+        const size_t off = (((size_t)n * WH + iy) * WW + pc) * WC + q * 4;
+        buf[j] = load_operand4(wide, valid ? off : 0, q * 4, valid);
+      }
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) acc[a][b][c] = 0.f;
-
-  // source pixel (iy+dy, ix+dx) contributes to output parity (py,px) through tap (ky,kx):
-  //   dy=0: py=0 -> ky=1 ; py=1 -> ky=2        dy=1: py=1 -> ky=0
-#pragma unroll
-  for (int dy = 0; dy < 2; ++dy) {
-#pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      const int sy = iy + dy, sx = ix + dx;
-      const bool valid = sy < WH && sx < WW;
-      const size_t off = (((size_t)n * WH + sy) * WW + sx) * WC;
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 v4 = load_operand4(wide, off + c4 * 4, c4 * 4, valid);
-        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-        for (int py = dy; py < 2; ++py) {
-          const int ky = dy ? 0 : (py ? 2 : 1);
-#pragma unroll
-          for (int px = dx; px < 2; ++px) {
-            const int kx = dx ? 0 : (px ? 2 : 1);
-#pragma unroll
-            for (int co = 0; co < 3; ++co) {
-              const float4 wv = *reinterpret_cast<const float4*>(&Wsm[ky * 3 + kx][co][c4 * 4]);
-              acc[py][px][co] = fmaf(v[0], wv.x, fmaf(v[1], wv.y, fmaf(v[2], wv.z, fmaf(v[3], wv.w, acc[py][px][co]))));
-            }
-          }
-        }
+      for (int j = 0; j < ITER; ++j) {
+        const int i = tid + j * TT_THREADS;
+        if (i >= UNITS) break;
+        const int q = i & 7, p = i >> 3;
+        *reinterpret_cast<float4*>(as + p * 32 + ((q ^ (p & 7)) << 2)) = buf[j];
       }
     }
-  }
-  float err = 0.f;
+    __syncthreads();
+    // wide pixel (warp, lane): acc[py][px][co] of its 2x2 output quad
+    float acc[2][2][3];
 #pragma unroll
-  for (int co = 0; co < 3; ++co) {
-    const float b = __ldg(bias + co);
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int py = 0; py < 2; ++py) {
-      const size_t o = (((size_t)n * 3 + co) * TH + 2 * iy + py) * TW + 2 * ix;
-      const float s0 = 1.f / (1.f + expf(-(acc[py][0][co] + b)));
-      const float s1 = 1.f / (1.f + expf(-(acc[py][1][co] + b)));
-      *reinterpret_cast<float2*>(x_hat + o) = make_float2(s0, s1);
-      if (x) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(x + o));
-        err += (s0 - t.x) * (s0 - t.x) + (s1 - t.y) * (s1 - t.y);
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[a][b][c] = 0.f;
+    // source pixel (iy+dy, ix+dx) contributes to output parity (py,px) through tap (ky,kx):
+    //   dy=0: py=0 -> ky=1 ; py=1 -> ky=2        dy=1: py=1 -> ky=0      (same for x)
+#pragma unroll 1
+    for (int q4 = 0; q4 < 8; ++q4) {
+      float4 v[2][2];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int p = (warp + dy) * AS_COLS + lane + dx;
+          v[dy][dx] = *reinterpret_cast<const float4*>(as + p * 32 + ((q4 ^ (p & 7)) << 2));
+        }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+          for (int py = dy; py < 2; ++py) {
+            const int ky = dy ? 0 : (py ? 2 : 1);
+#pragma unroll
+            for (int px = dx; px < 2; ++px) {
+              const int kx = dx ? 0 : (px ? 2 : 1);
+#pragma unroll
+              for (int co = 0; co < 3; ++co) {
+                const float4 wv = *reinterpret_cast<const float4*>(Wsm + ((ky * 3 + kx) * 3 + co) * 32 + q4 * 4);
+                const float4 vv = v[dy][dx];
+                acc[py][px][co] = fmaf(vv.x, wv.x, fmaf(vv.y, wv.y, fmaf(vv.z, wv.z, fmaf(vv.w, wv.w, acc[py][px][co]))));
+              }
+            }
+          }
+    }
+    const int ty0 = 2 * (tr * TILE_ROWS + warp);        // first of this thread's two thin rows
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      const float b = co == 0 ? b0 : (co == 1 ? b1 : b2);
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const size_t o = (((size_t)n * 3 + co) * TH + ty0 + py) * TW + 2 * lane;
+        const float s0 = 1.f / (1.f + expf(-(acc[py][0][co] + b)));
+        const float s1 = 1.f / (1.f + expf(-(acc[py][1][co] + b)));
+        *reinterpret_cast<float2*>(x_hat + o) = make_float2(s0, s1);
+        if (x) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(x + o));
+          err += (s0 - t.x) * (s0 - t.x) + (s1 - t.y) * (s1 - t.y);
+        }
       }
     }
   }
   if (x && sse) {
     err = warp_sum(err);
-    if (lane == 0) red[tid >> 5] = err;
+    if (lane == 0) red[warp] = err;
     __syncthreads();
-    if (tid == 0) atomicAdd(sse, (double)red[0] + (double)red[1] + (double)red[2] + (double)red[3]);
+    if (tid == 0) atomicAdd(sse, ((double)red[0] + (double)red[1]) + ((double)red[2] + (double)red[3]));
   }
 }
 
 int thin_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* bias, float* x_hat, const float* x,
                              double* sse, int batch, cudaStream_t st) {
-  k_thin_scatter_sigmoid<<<batch * 8, 128, 0, st>>>(wide, w, bias, x_hat, x, sse, batch);
-  AE_LAUNCH_CHECK();
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Weight gradient of either thin layer: dw[c32][k] = sum_pixels wide(p,c32) * patch(p,k), k=(c3,ky,kx).
-// Persistent blocks of 288 threads; per 128-pixel tile the operands are staged in shared memory,
-// each thread owns a 4(c32) x 3(k) register tile for one quarter of the tile's pixels; the four
-// quarters are summed through shared memory, every block writes one partial, a fixed-order
-// reduction kernel sums the partials (deterministic).
-// ---------------------------------------------------------------------------------------------
-static constexpr int TW_THREADS = 288;
-static constexpr int TW_PART = 868;  // 864 weights + 3 thin-bias sums + 1 pad
-
-__global__ void __launch_bounds__(TW_THREADS) k_thin_wgrad(Operand wide, Operand thin, float* __restrict__ partial,
-                                                           int batch) {
-  __shared__ __align__(16) float Ws[128][36];
-  __shared__ float Ts[128][28];
-  __shared__ float red[4][864];
-  __shared__ float bsum[TW_THREADS / 32][3];
-  const int tid = threadIdx.x;
-  const int grp = tid / 72, u = tid - grp * 72;
-  const int c4 = u & 7, kg = u >> 3;
-  float acc[4][3];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) acc[i][j] = 0.f;
-  float bs[3] = {0.f, 0.f, 0.f};
-
-  const int tiles = batch * 8;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int m0 = tile * 128;
-    for (int i = tid; i < 128 * 8; i += TW_THREADS) {
-      const int p = i >> 3, q = i & 7;
-      *reinterpret_cast<float4*>(&Ws[p][q * 4]) = load_operand4(wide, (size_t)(m0 + p) * WC + q * 4, q * 4, true);
-    }
-    for (int i = tid; i < 128 * 27; i += TW_THREADS) {
-      const int p = i / 27, k = i - p * 27;
-      const int m = m0 + p;
-      const int ox = m & 31, oy = (m >> 5) & 31, n = m >> 10;
-      const int c3 = k / 9, r = k - c3 * 9, ky = r / 3, kx = r - ky * 3;
-      const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
-      float v = 0.f;
-      if (iy >= 0 && ix >= 0) v = thin_value(thin, (((size_t)n * 3 + c3) * TH + iy) * TW + ix);
-      Ts[p][k] = v;
-      // taps (ky,kx) in {1,2}^2 enumerate the 2x2 big-image quad owned by this small pixel exactly once
-      if (ky >= 1 && kx >= 1) {
-        if (c3 == 0) bs[0] += v; else if (c3 == 1) bs[1] += v; else bs[2] += v;
-      }
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int pp = 0; pp < 32; ++pp) {
-      const int p = grp * 32 + pp;
-      const float4 a = *reinterpret_cast<const float4*>(&Ws[p][c4 * 4]);
-      const float b0 = Ts[p][kg * 3 + 0], b1 = Ts[p][kg * 3 + 1], b2 = Ts[p][kg * 3 + 2];
-      acc[0][0] = fmaf(a.x, b0, acc[0][0]); acc[0][1] = fmaf(a.x, b1, acc[0][1]); acc[0][2] = fmaf(a.x, b2, acc[0][2]);
-      acc[1][0] = fmaf(a.y, b0, acc[1][0]); acc[1][1] = fmaf(a.y, b1, acc[1][1]); acc[1][2] = fmaf(a.y, b2, acc[1][2]);
-      acc[2][0] = fmaf(a.z, b0, acc[2][0]); acc[2][1] = fmaf(a.z, b1, acc[2][1]); acc[2][2] = fmaf(a.z, b2, acc[2][2]);
-      acc[3][0] = fmaf(a.w, b0, acc[3][0]); acc[3][1] = fmaf(a.w, b1, acc[3][1]); acc[3][2] = fmaf(a.w, b2, acc[3][2]);
-    }
-    __syncthreads();
+  const size_t smem = sizeof(float) * (AS_ROWS * AS_COLS * 32 + 27 * 32);
+  static bool attr_done = false;
+  if (!attr_done) {
+    AE_CUDA(cudaFuncSetAttribute(k_thin_scatter_sigmoid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) red[grp][(c4 * 4 + i) * 27 + kg * 3 + j] = acc[i][j];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float s = warp_sum(bs[c]);
-    if ((tid & 31) == 0) bsum[tid >> 5][c] = s;
-  }
-  __syncthreads();
-  float* dst = partial + (size_t)blockIdx.x * TW_PART;
-  for (int i = tid; i < 864; i += TW_THREADS) dst[i] = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);
-  if (tid < 3) {
-    float s = 0.f;
-    for (int wq = 0; wq < TW_THREADS / 32; ++wq) s += bsum[wq][tid];
-    dst[864 + tid] = s;
-  }
-  if (tid == 3) dst[867] = 0.f;
-}
-
-__global__ void k_thin_wgrad_reduce(const float* __restrict__ partial, int nparts, float* __restrict__ dw,
-                                    float* __restrict__ dbias) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 867) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += __ldg(partial + (size_t)p * TW_PART + i);
-  if (i < 864) dw[i] = s;
-  else if (dbias) dbias[i - 864] = s;
-}
-
-static int thin_wgrad_blocks(int batch) {
-  const int tiles = batch * 8;
-  return tiles < 296 ? tiles : 296;
-}
-size_t thin_wgrad_workspace_bytes(int batch) { return (size_t)thin_wgrad_blocks(batch) * TW_PART * sizeof(float); }
-
-int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes,
-               int batch, cudaStream_t st) {
-  const int blocks = thin_wgrad_blocks(batch);
-  AE_CHECK(bytes >= (size_t)blocks * TW_PART * sizeof(float), "thin_wgrad: workspace too small");
-  k_thin_wgrad<<<blocks, TW_THREADS, 0, st>>>(wide, thin, static_cast<float*>(partials), batch);
-  AE_LAUNCH_CHECK();
-  k_thin_wgrad_reduce<<<(867 + 127) / 128, 128, 0, st>>>(static_cast<const float*>(partials), blocks, dw, dbias);
+  k_thin_scatter_sigmoid<<<thin_blocks(batch), TT_THREADS, smem, st>>>(wide, w, bias, x_hat, x, sse, batch);
   AE_LAUNCH_CHECK();
   return 0;
 }

@@ -133,6 +133,9 @@ struct alignas(64) TmaRow {
   int bx, by, bn;           // pixel box of one 128-row tile
 };
 
+// Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A tile is (phase, n-tile, m-tile) with
+// the m-tile fastest.  The accumulator is double-buffered in tensor memory, so the epilogue of tile i overlaps the
+// TMA loads and MMAs of tile i+1, and barrier / TMEM set-up is paid once per CTA.
 template <int FAMILY, int NT, int KC, int NSPLIT, int STAGES>
 __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constant__ TmaRow q) {
   constexpr int ROWB = KC * 2;                                // bytes per shared-memory row
@@ -141,66 +144,82 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
   constexpr uint32_t A_BYTES = NSPLIT * A_PLANE, B_BYTES = NSPLIT * B_PLANE;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t SBO = 8 * ROWB;
+  constexpr uint32_t TMEM_COLS = 2 * NT;                      // two accumulators
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ float sStat[2][NT];
 
   const Geom g = q.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TILE_M;
-  const int ntile = blockIdx.y;
-  int py = 0, px = 0, kc_off = 0, nkc;
-  if (FAMILY == FAM_DGRAD) {
-    const int phase = blockIdx.z;
-    py = phase >> 1; px = phase & 1;
-    nkc = (1 + py) * (1 + px) * q.cpt;
-    kc_off = (phase == 0 ? 0 : phase == 1 ? 1 : phase == 2 ? 3 : 5) * q.cpt;
-  } else {
-    nkc = 9 * q.cpt;
-  }
+  const int tiles_m = (q.M + TILE_M - 1) / TILE_M, tiles_n = q.N / NT;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int num_tiles = tiles_mn * (FAMILY == FAM_DGRAD ? 4 : 1);
+
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  const uint32_t accum_bar = bar0 + 8u * (2 * STAGES);
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     fence_barrier_init();
   }
   if (tid >= 64 && tid < 64 + NT) { sStat[0][tid - 64] = 0.f; sStat[1][tid - 64] = 0.f; }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), NT);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  // tile -> (phase, ntile, m0, number of K chunks, first chunk inside the weight pack)
+  auto decode = [&](int tile, int& phase, int& ntile, int& m0, int& nkc, int& kc_off) {
+    phase = tile / tiles_mn;
+    const int rem = tile - phase * tiles_mn;
+    ntile = rem / tiles_m;
+    m0 = (rem - ntile * tiles_m) * TILE_M;
+    if (FAMILY == FAM_DGRAD) {
+      const int py = phase >> 1, px = phase & 1;
+      nkc = (1 + py) * (1 + px) * q.cpt;
+      kc_off = (phase == 0 ? 0 : phase == 1 ? 1 : phase == 2 ? 3 : 5) * q.cpt;
+    } else {
+      nkc = 9 * q.cpt;
+      kc_off = 0;
+    }
+  };
+
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
     if (lane == 0) {
-      // tile origin in the small image
       const int P = g.Hs * g.Ws;
-      const int n0 = m0 >> (g.lHs + g.lWs);
-      const int y0 = (m0 & (P - 1)) >> g.lWs;
-      const uint8_t* wsrc = q.wtiles + ((size_t)ntile * q.wchunks + kc_off) * B_BYTES;
-      for (int it = 0; it < nkc; ++it) {
-        const int s = it % STAGES, round = it / STAGES;
-        if (round > 0) mbar_wait(empty_bar(s), (round - 1) & 1);
-        const uint32_t a_dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
-        const int tap = it / q.cpt, c0 = (it - tap * q.cpt) * KC;
-        if (FAMILY == FAM_FPROP) {
-          const int ky = tap / 3, kx = tap - ky * 3;
-          const int pmap = ((ky + 1) & 1) * 2 + ((kx + 1) & 1);       // parity lattice of source row 2*oy-1+ky
-          tma_load_5d(a_dst, &q.amap[pmap], c0, (kx == 0) ? -1 : 0, y0 + ((ky == 0) ? -1 : 0), n0, 0, full_bar(s));
-        } else {
-          const int a = tap / (1 + px), b = tap - a * (1 + px);
-          const int dy = (py && a == 0) ? 1 : 0, dx = (px && b == 0) ? 1 : 0;   // source = (y + dy, x + dx)
-          tma_load_5d(a_dst, &q.amap[0], c0, dx, y0 + dy, n0, 0, full_bar(s));
+      uint32_t gc = 0;                                        // chunk counter over all tiles of this CTA
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int phase, ntile, m0, nkc, kc_off;
+        decode(tile, phase, ntile, m0, nkc, kc_off);
+        const int py = phase >> 1, px = phase & 1;
+        const int n0 = m0 >> (g.lHs + g.lWs);
+        const int y0 = (m0 & (P - 1)) >> g.lWs;
+        const uint8_t* wsrc = q.wtiles + ((size_t)ntile * q.wchunks + kc_off) * B_BYTES;
+        for (int it = 0; it < nkc; ++it, ++gc) {
+          const uint32_t s = gc % STAGES, round = gc / STAGES;
+          if (round > 0) mbar_wait(empty_bar(s), (round - 1) & 1);
+          const uint32_t a_dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+          const int tap = it / q.cpt, c0 = (it - tap * q.cpt) * KC;
+          if (FAMILY == FAM_FPROP) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const int pmap = ((ky + 1) & 1) * 2 + ((kx + 1) & 1);     // parity lattice of source row 2*oy-1+ky
+            tma_load_5d(a_dst, &q.amap[pmap], c0, (kx == 0) ? -1 : 0, y0 + ((ky == 0) ? -1 : 0), n0, 0, full_bar(s));
+          } else {
+            const int a = tap / (1 + px), b = tap - a * (1 + px);
+            const int dy = (py && a == 0) ? 1 : 0, dx = (px && b == 0) ? 1 : 0;   // source = (y + dy, x + dx)
+            tma_load_5d(a_dst, &q.amap[0], c0, dx, y0 + dy, n0, 0, full_bar(s));
+          }
+          bulk_copy_g2s(a_dst + A_BYTES, wsrc + (size_t)it * B_BYTES, B_BYTES, full_bar(s));
         }
-        bulk_copy_g2s(a_dst + A_BYTES, wsrc + (size_t)it * B_BYTES, B_BYTES, full_bar(s));
       }
     }
     __syncwarp();
@@ -208,102 +227,126 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(NT, 0, 0);
-      for (int it = 0; it < nkc; ++it) {
-        const int s = it % STAGES, round = it / STAGES;
-        mbar_wait(full_bar(s), round & 1);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t b0 = a0 + A_BYTES;
+      uint32_t gc = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        int phase, ntile, m0, nkc, kc_off;
+        decode(tile, phase, ntile, m0, nkc, kc_off);
+        const uint32_t ab = ti & 1, ar = ti >> 1;
+        if (ar > 0) { mbar_wait(tempty_bar(ab), (ar - 1) & 1); tc_fence_after(); }
+        const uint32_t acc = tmem_base + ab * NT;
+        for (int it = 0; it < nkc; ++it, ++gc) {
+          const uint32_t s = gc % STAGES, round = gc / STAGES;
+          mbar_wait(full_bar(s), round & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t b0 = a0 + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < KC / 16; ++kk) {
-          const uint64_t ah = make_desc(a0 + kk * 32, 16, SBO, ROWB), bh = make_desc(b0 + kk * 32, 16, SBO, ROWB);
-          umma_bf16(tmem_base, ah, bh, idesc, (it | kk) != 0);
-          if (NSPLIT == 2) {
-            const uint64_t al = make_desc(a0 + A_PLANE + kk * 32, 16, SBO, ROWB);
-            const uint64_t bl = make_desc(b0 + B_PLANE + kk * 32, 16, SBO, ROWB);
-            umma_bf16(tmem_base, ah, bl, idesc, 1);
-            umma_bf16(tmem_base, al, bh, idesc, 1);
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint64_t ah = make_desc(a0 + kk * 32, 16, SBO, ROWB), bh = make_desc(b0 + kk * 32, 16, SBO, ROWB);
+            umma_bf16(acc, ah, bh, idesc, (it | kk) != 0);
+            if (NSPLIT == 2) {
+              const uint64_t al = make_desc(a0 + A_PLANE + kk * 32, 16, SBO, ROWB);
+              const uint64_t bl = make_desc(b0 + B_PLANE + kk * 32, 16, SBO, ROWB);
+              umma_bf16(acc, ah, bl, idesc, 1);
+              umma_bf16(acc, al, bh, idesc, 1);
+            }
           }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(ab));
       }
-      umma_commit(accum_bar);
     }
     __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5; warp w owns TMEM lanes 32*(w%4) ..) =====================
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < q.M;
+    const int et = tid - 64;
     const Epilogue e = q.epi;
-    size_t orow = 0;
-    if (row_ok) {
-      if (FAMILY == FAM_DGRAD) {
-        const int x = m & (g.Ws - 1), y = (m >> g.lWs) & (g.Hs - 1), nn = m >> (g.lWs + g.lHs);
-        orow = (((size_t)nn * (2 * g.Hs) + 2 * y + py) * (2 * g.Ws) + 2 * x + px) * q.N;
-      } else {
-        orow = (size_t)m * q.N;
+    const bool do_stats = e.mode != AE_EPI_STORE && e.stats != nullptr;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      int phase, ntile, m0, nkc, kc_off;
+      decode(tile, phase, ntile, m0, nkc, kc_off);
+      const int py = phase >> 1, px = phase & 1;
+      const uint32_t ab = ti & 1;
+      const int m = m0 + row;
+      const bool row_ok = m < q.M;
+      size_t orow = 0;
+      if (row_ok) {
+        if (FAMILY == FAM_DGRAD) {
+          const int x = m & (g.Ws - 1), y = (m >> g.lWs) & (g.Hs - 1), nn = m >> (g.lWs + g.lHs);
+          orow = (((size_t)nn * (2 * g.Hs) + 2 * y + py) * (2 * g.Ws) + 2 * x + px) * q.N;
+        } else {
+          orow = (size_t)m * q.N;
+        }
       }
-    }
+      mbar_wait(tfull_bar(ab), (ti >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-    for (int col0 = 0; col0 < NT; col0 += 32) {
-      const int n = ntile * NT + col0;                 // global output channel
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
-      float s2[32];
-      if (e.mode == AE_EPI_RELUBWD_STATS) {
+      for (int col0 = 0; col0 < NT; col0 += 32) {
+        const int n = ntile * NT + col0;                 // global output channel
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + ab * NT + (uint32_t)col0, v);
+        if (col0 + 32 >= NT) {                           // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(ab));
+        }
+        float s2[32];
+        if (e.mode == AE_EPI_RELUBWD_STATS) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok) yv = __ldg(reinterpret_cast<const float4*>(e.y + orow + n) + j4);
-          const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok) yv = __ldg(reinterpret_cast<const float4*>(e.y + orow + n) + j4);
+            const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = (n + j4 * 4 + j) % e.C;
-            const float z = fmaf(ya[j], __ldg(e.bnc + AE_BNC_SCALE * e.C + ch), __ldg(e.bnc + AE_BNC_SHIFT * e.C + ch));
-            const float d = (row_ok && z > 0.f) ? v[j4 * 4 + j] : 0.f;
-            v[j4 * 4 + j] = d;
-            s2[j4 * 4 + j] = d * ((ya[j] - __ldg(e.bnc + AE_BNC_MEAN * e.C + ch)) * __ldg(e.bnc + AE_BNC_RSTD * e.C + ch));
+            for (int j = 0; j < 4; ++j) {
+              const int ch = (n + j4 * 4 + j) % e.C;
+              const float z = fmaf(ya[j], __ldg(e.bnc + AE_BNC_SCALE * e.C + ch), __ldg(e.bnc + AE_BNC_SHIFT * e.C + ch));
+              const float d = (row_ok && z > 0.f) ? v[j4 * 4 + j] : 0.f;
+              v[j4 * 4 + j] = d;
+              s2[j4 * 4 + j] = d * ((ya[j] - __ldg(e.bnc + AE_BNC_MEAN * e.C + ch)) * __ldg(e.bnc + AE_BNC_RSTD * e.C + ch));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float d = v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f);
+            d = row_ok ? d : 0.f;
+            v[j] = d;
+            s2[j] = d * d;
           }
         }
-      } else {
+        if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float d = v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f);
-          d = row_ok ? d : 0.f;
-          v[j] = d;
-          s2[j] = d * d;
+          for (int j4 = 0; j4 < 8; ++j4)
+            reinterpret_cast<float4*>(q.out + orow + n)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+        if (do_stats) {
+          const float a = warp_colsum32_tc(v, lane);
+          const float b = warp_colsum32_tc(s2, lane);
+          atomicAdd(&sStat[0][col0 + lane], a);
+          atomicAdd(&sStat[1][col0 + lane], b);
         }
       }
-      if (row_ok) {
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          reinterpret_cast<float4*>(q.out + orow + n)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+      if (do_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < NT) {
+          const int ch = (ntile * NT + et) % e.C;
+          atomicAdd(e.stats + ch, (double)sStat[0][et]);
+          atomicAdd(e.stats + e.C + ch, (double)sStat[1][et]);
+          sStat[0][et] = 0.f; sStat[1][et] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      if (e.mode != AE_EPI_STORE && e.stats) {
-        const float a = warp_colsum32_tc(v, lane);
-        const float b = warp_colsum32_tc(s2, lane);
-        atomicAdd(&sStat[0][col0 + lane], a);
-        atomicAdd(&sStat[1][col0 + lane], b);
-      }
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int et = tid - 64;
-    if (e.mode != AE_EPI_STORE && e.stats && et < NT) {
-      const int ch = (ntile * NT + et) % e.C;
-      atomicAdd(e.stats + ch, (double)sStat[0][et]);
-      atomicAdd(e.stats + e.C + ch, (double)sStat[1][et]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, NT);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -386,7 +429,9 @@ static int launch_row(const TmaRow& q, dim3 grid, cudaStream_t st) {
     AE_CUDA(cudaFuncSetAttribute(k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES><<<grid, RG_THREADS, smem, st>>>(q);
+  const int tiles = (int)(grid.x * grid.y * grid.z);
+  const int ctas = tiles < 2 * 148 ? tiles : 2 * 148;       // ~97 KB of shared memory per CTA: two CTAs per SM
+  k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES><<<ctas, RG_THREADS, smem, st>>>(q);
   AE_LAUNCH_CHECK();
   return 0;
 }

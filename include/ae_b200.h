@@ -149,6 +149,11 @@ int ae_thin_wgrad(const ae_operand_t* wide, const ae_operand_t* thin, float* dw 
                   float* dbias_thin /*[3] or NULL*/, void* partials, size_t partials_bytes, int batch,
                   ae_stream_t stream);
 size_t ae_thin_wgrad_workspace_bytes(int batch);
+/* ae_thin_gather_fwd (data gradient, `epi` = RELUBWD) and ae_thin_wgrad of ConvTranspose2d(32,3) in one pass over the
+ * thin operand (autograd of NB:628-629); same workspace as ae_thin_wgrad */
+int ae_thin_bwd_fused(const ae_operand_t* wide, const ae_operand_t* thin, const float* w /*[32,3,3,3]*/,
+                      const ae_epilogue_t* epi, float* out_wide, float* dw, float* dbias_thin, void* partials,
+                      size_t partials_bytes, int batch, ae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNorm statistics (NB:505-517, NB:617-625; torch defaults eps 1e-5, momentum 0.1).

@@ -208,6 +208,15 @@ def test_thin_layers(batch):
     mask = (t3 * v(0) + v(1)) > 0
     ref_dz = a3r.grad * mask
     assert float((gu.nchw(dz).cpu() - ref_dz).abs().max()) <= 2e-5 * float(a3r.grad.abs().max())
+    # the fused backward (one pass over x / x_hat) must reproduce both results
+    dw2, db2, dz2 = torch.empty_like(dw), torch.empty_like(db), torch.empty_like(dz)
+    stats2 = torch.zeros_like(stats)
+    epf = gu.epilogue(_lib.EPI_RELUBWD_STATS, None, t3d, bncd, stats2)
+    _lib.check(gu.lib().ae_thin_bwd_fused(C.byref(opw), C.byref(opt), gu.p(w4d), C.byref(epf), gu.p(dz2), gu.p(dw2), gu.p(db2),
+                                         gu.p(part), nb, batch, gu.stream()))
+    torch.cuda.synchronize()
+    assert gu.rel(dw2, dw) <= 1e-6 and gu.rel(db2, db) <= 1e-6 and gu.rel(dz2, dz) <= 1e-6
+    assert gu.rel(stats2, stats) <= 1e-6
 
 
 def test_bn_finalize_and_backward_coefficients():
