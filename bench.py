@@ -135,6 +135,87 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+# Roofline of the dominant kernel: the TMA-fed tcgen05 row GEMM (k_tma_rowgemm, 12 launches per step, the largest
+# share of the step in profiles/*launches*).  Timed on its own with CUDA events on the launching stream, on the
+# geometry of its most frequent instance (ConvTranspose2d 128->64 forward, NB:620: 8x8 -> 16x16 pixels), inputs
+# rotating over more buffers than fit in L2.  Algorithmic bytes per launch: the operand
+# planes once + the packed weights once + the fp32 output once.
+# --------------------------------------------------------------------------------------------------
+TRAFFIC_NCU = {"fp32": 27.3e6, "bf16": None}    # dram__bytes_read+write per launch, profiles/r1_rowgemm_dgrad64_full.txt
+
+
+def kernel_roofline(dev, B, precision, iters=60):
+    import ctypes as C
+    from ae_b200 import _lib
+    lib = _lib.load()
+    prec = _lib.PREC_FP32 if precision == "fp32" else _lib.PREC_BF16
+    nsplit = 2 if precision == "fp32" else 1
+    hs, cb, cs = 8, 64, 128
+    M = B * hs * hs
+    g = _lib.ConvGeom(B, hs, hs, cb, cs)
+    w = torch.randn(cs, cb, 3, 3, device=dev) / (9 * cs / 4) ** 0.5
+    nbytes = lib.ae_packed_weight_bytes(cs, cb, prec, _lib.BACKEND_TC)
+    raw = torch.zeros(2 * nbytes + 2048, dtype=torch.uint8, device=dev)
+    base = (raw.data_ptr() + 1023) & ~1023
+    pk_f, pk_d = C.c_void_p(base), C.c_void_p((base + nbytes + 1023) & ~1023)
+    _lib.check(lib.ae_pack_conv_weight(_lib.ptr(w), cs, cb, pk_f, pk_d, prec, _lib.BACKEND_TC, _lib.stream_ptr()))
+    bias = torch.zeros(cb, device=dev)
+    stats = torch.zeros(2 * cb, dtype=torch.float64, device=dev)
+    a_bytes, o_bytes, w_bytes = M * cs * 2 * nsplit, 4 * M * cb * 4, 9 * cs * cb * 2 * nsplit
+    n_rot = max(2, int(140e6 // (a_bytes + o_bytes)) + 1)
+    planes = [(torch.randn(nsplit * M * cs, device=dev) * 0.5).to(torch.bfloat16) for _ in range(n_rot)]
+    outs = [torch.empty(B, 2 * hs, 2 * hs, cb, device=dev) for _ in range(n_rot)]
+    ep = _lib.Epilogue(_lib.EPI_BIAS_STATS, _lib.ptr(bias), None, None, _lib.ptr(stats))
+
+    def launch(i):
+        op = _lib.Operand(_lib.ptr(planes[i % n_rot]), None, None, 0.0, _lib.OP_SPLIT_BF16)
+        _lib.check(lib.ae_conv2d_s2_dgrad(C.byref(g), C.byref(op), pk_d, C.byref(ep), _lib.ptr(outs[i % n_rot]), prec,
+                                          _lib.BACKEND_TC, _lib.stream_ptr()))
+
+    for i in range(5):
+        launch(i)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for i, (e0, e1) in enumerate(evs):
+        e0.record()
+        launch(i)
+        e1.record()
+    torch.cuda.synchronize()
+    ts = sorted(e0.elapsed_time(e1) * 1e-3 for e0, e1 in evs)
+    t = sum(ts) / len(ts)
+    peaks = measured_peaks()
+    alg = a_bytes + o_bytes + w_bytes
+    flop = 2.0 * M * 9 * cs * cb
+    return {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "frac": alg / t / 1e9 / peaks["hbm"],
+            "traffic": TRAFFIC_NCU.get(precision), "kernel": "k_tma_rowgemm<DGRAD,NT=64> (ConvTranspose2d 128->64 forward, batch %d)" % B,
+            "algorithmic_bytes": alg, "avg_launch_us": t * 1e6, "median_launch_us": ts[len(ts) // 2] * 1e6, "launches_timed": iters,
+            "tensor_tflops": flop / t / 1e12, "tensor_frac_of_burst": flop / t / 1e12 / peaks["tf_burst"],
+            "peak_source": peaks["source"], "l2": f"inputs/outputs rotate over {n_rot} buffer sets ({n_rot * (a_bytes + o_bytes) / 1e6:.0f} MB > L2)"}
+
+
+def inference_rate(dev, precision, backend, batch=4096, iters=20):
+    """BASELINE's second metric: encoder + MLP inference images/s (clf(enc(x)).argmax(1), eval mode), device-resident
+    inputs rotating over > L2, CUDA events."""
+    import ae_b200
+    torch.manual_seed(1)
+    ae = ae_b200.SupervisedAutoencoder(64, 10, precision=precision, backend=backend).to(dev).eval()
+    clf = ae_b200.MLP(64, 10).to(dev).eval()
+    xs = [torch.rand(batch, 3, 64, 64, device=dev) for _ in range(3)]     # 3 x 201 MB
+    for i in range(3):
+        ae_b200.encode_predict(ae.enc, clf, xs[i % 3])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        ae_b200.encode_predict(ae.enc, clf, xs[i % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / iters
+    return {"metric": "encoder+MLP infer img/s", "value": batch / t, "unit": "images/s", "batch": batch, "ms_per_batch": t * 1e3,
+            "dtype": precision}
+
+
+# --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
     import ae_b200
@@ -197,32 +278,27 @@ def run_ours(args):
     value = B * world * args.steps / (ms * 1e-3)
     final_loss = [float(v) for v in stepper.loss[:3].cpu()]
 
-    # ---- end to end: pinned host batches in, loss out, every step ----
-    loss_host = torch.zeros(4).pin_memory()
-    losses = []
-
-    def e2e_steps(k, i0=0):
+    # ---- end to end: pinned host batches in, loss out, every step (public API: TrainStep.run_batches) ----
+    def host_batches(k, i0=0):
         for i in range(k):
-            stepper.load(xs_h[(i0 + i) % n_rot], ys_h[(i0 + i) % n_rot])
-            stepper.run()
-            with torch.cuda.stream(stream):
-                loss_host.copy_(stepper.loss, non_blocking=True)
-            stream.synchronize()
-            losses.append(float(loss_host[0]))
+            yield xs_h[(i0 + i) % n_rot], ys_h[(i0 + i) % n_rot]
 
-    e2e_steps(0 if args.no_e2e else min(args.warmup, 3))
+    stepper.run_batches(host_batches(0 if args.no_e2e else min(args.warmup, 3)))
     barrier()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record(stream)
     w0 = time.perf_counter()
-    e2e_steps(1 if args.no_e2e else args.steps)
-    t1.record(stream)
-    barrier()
+    losses = stepper.run_batches(host_batches(1 if args.no_e2e else args.steps))
+    torch.cuda.synchronize()
     wall = time.perf_counter() - w0
+    barrier()
     tt = torch.tensor([wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e = B * world * args.steps / float(tt.item())
+    e2e = B * world * (1 if args.no_e2e else args.steps) / float(tt.item())
+    assert len(losses) == (1 if args.no_e2e else args.steps) and all(torch.isfinite(l).all() for l in losses)
+
+    # ---- the dominant kernel on its own stream-ordered CUDA events (roofline), and encoder+MLP inference ----
+    roof = None if args.no_roofline else kernel_roofline(dev, B, args.precision)
+    infer = None if args.no_roofline else inference_rate(dev, args.precision, args.backend)
 
     peaks = measured_peaks()
     flops = FLOP_PER_IMAGE_TRAIN * B
@@ -241,10 +317,12 @@ def run_ours(args):
         "gpu_launches": int(stepper.num_kernels) * args.steps,
         "kernels_per_step": int(stepper.num_kernels),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": flops / step_s / 1e12, "peak": peaks["tf"], "unit": "TFLOP/s",
-                     "frac": flops / step_s / 1e12 / peaks["tf"], "traffic": None, "peak_source": peaks["source"],
-                     "scope": "whole step (181.9 MFLOP/image x batch / step time)"},
+        "step_tflops": flops / step_s / 1e12,
     }
+    if roof is not None:
+        line["roofline"] = roof
+    if infer is not None:
+        line["inference"] = infer
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -270,6 +348,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("AE_B200_PRECISION", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--backend", default=os.environ.get("AE_B200_BACKEND", "tc"), choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the stand-alone kernel timing and the inference leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the end-to-end leg (its number is then meaningless)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -66,6 +66,64 @@ class TrainStep:
         cur.wait_stream(self.stream)
         return self.loss[:3]
 
+    def run_batches(self, batches, depth: int = 2):
+        """The loop NB:2672-2688 over an iterable of (imgs, labels) HOST batches (pinned memory for real overlap),
+        software-pipelined: the H2D copy of batch i+1 runs on a copy stream while the graph of batch i executes, and
+        the loss of batch i is read back (D2H, pinned) while batch i+1 runs.  Every batch is copied host->device and
+        every loss device->host; nothing is skipped.  Returns the list of [loss, mse, ce] host tensors."""
+        dev = self.device
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [(torch.empty_like(self.x), torch.empty_like(self.y)) for _ in range(depth)]
+            self._staged = [torch.cuda.Event() for _ in range(depth)]
+            self._consumed = [torch.cuda.Event() for _ in range(depth)]
+            self._loss_host = [torch.zeros(4).pin_memory() for _ in range(depth)]
+            self._loss_done = [torch.cuda.Event() for _ in range(depth)]
+        cs, ms = self._copy_stream, self.stream
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        ms.wait_stream(torch.cuda.current_stream(dev))
+        out, pending = [], []
+        it = iter(batches)
+
+        def stage(i, batch):
+            sx, sy = self._stage[i % depth]
+            with torch.cuda.stream(cs):
+                if i >= depth:
+                    cs.wait_event(self._consumed[i % depth])      # the step that used this staging slot has copied it out
+                sx.copy_(batch[0], non_blocking=True)
+                sy.copy_(batch[1], non_blocking=True)
+                self._staged[i % depth].record(cs)
+
+        nxt = next(it, None)
+        i = 0
+        if nxt is not None:
+            stage(0, nxt)
+        while nxt is not None:
+            cur_i = i
+            nxt = next(it, None)
+            if nxt is not None:
+                stage(cur_i + 1, nxt)                              # overlaps the graph launched below
+            sx, sy = self._stage[cur_i % depth]
+            with torch.cuda.stream(ms):
+                ms.wait_event(self._staged[cur_i % depth])
+                self.x.copy_(sx, non_blocking=True)                # device-to-device, a few microseconds
+                self.y.copy_(sy, non_blocking=True)
+                self._consumed[cur_i % depth].record(ms)
+                self.run()
+                if len(pending) >= depth:                          # the host slot is free once its loss was consumed
+                    j = pending.pop(0)
+                    self._loss_done[j % depth].synchronize()
+                    out.append(self._loss_host[j % depth][:3].clone())
+                self._loss_host[cur_i % depth].copy_(self.loss, non_blocking=True)
+                self._loss_done[cur_i % depth].record(ms)
+            pending.append(cur_i)
+            i += 1
+        for j in pending:
+            self._loss_done[j % depth].synchronize()
+            out.append(self._loss_host[j % depth][:3].clone())
+        torch.cuda.current_stream(dev).wait_stream(ms)
+        return out
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):
