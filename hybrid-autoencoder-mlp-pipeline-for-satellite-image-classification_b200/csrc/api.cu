@@ -73,7 +73,7 @@ size_t ae_split_operand_bytes(int64_t count, int precision) { return (size_t)cou
 
 int ae_split_operand(const ae_operand_t* op, int channels, int64_t count, void* planes, int precision, ae_stream_t stream) {
   AE_CHECK(op && op->src && planes && channels >= 8 && count >= 8, "ae_split_operand: bad argument");
-  return tma_split_operand(make_operand(op, channels), count, planes, nsplit_of(precision), (cudaStream_t)stream);
+  return tma_split_operand(make_operand(op, channels), count, planes, nsplit_of(precision), nullptr, (cudaStream_t)stream);
 }
 
 int ae_pack_conv_weight(const float* w, int cs, int cb, void* packed_fwd, void* packed_dgrad, int precision, int backend,

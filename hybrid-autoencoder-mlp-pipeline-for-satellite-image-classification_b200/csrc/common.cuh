@@ -65,6 +65,25 @@ struct Epilogue {
   int C;             // channels of the BN this epilogue feeds (channel = n % C)
 };
 
+// BatchNorm coefficient job a consumer kernel can run in its prologue instead of a separate launch:
+//   BN_JOB_FINALIZE: ae_bn_finalize (statistics -> scale/shift/mean/rstd, running-stat update)
+//   BN_JOB_BWD     : ae_bn_bwd_reduce (sums -> A/B/C, dgamma, dbeta)
+enum { BN_JOB_NONE = 0, BN_JOB_FINALIZE = 1, BN_JOB_BWD = 2 };
+struct BnJob {
+  int kind;
+  const double* stats;
+  double count;
+  const float* gamma;
+  const float* beta;
+  float* rmean;
+  float* rvar;
+  float* bnc;
+  float* dgamma;
+  float* dbeta;
+  int C;
+  int training;
+};
+
 struct Geom {
   int B, Hs, Ws, Cb, Cs;
   int lHs, lWs;      // log2
@@ -205,7 +224,8 @@ int permute_vector(const float* src, int n, int permC, int permHW, float* dst, c
 // tcgen05 + TMA path (tma_gemm.cu)
 size_t tma_packed_bytes(int Cs, int Cb, int nsplit);
 int tma_pack_conv(const float* w, int Cs, int Cb, int nsplit, void* fwd, void* dgrad, cudaStream_t st);
-int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit, cudaStream_t st);
+int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit, const BnJob* job, cudaStream_t st);
+int run_bn_job(const BnJob& job, cudaStream_t st);   // the same job as stand-alone launches
 int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);   // p.A: AE_OP_SPLIT_BF16
 bool tma_rowgemm_supported(const RowGemm& p);
 bool tma_wgrad_supported(const Geom& g);

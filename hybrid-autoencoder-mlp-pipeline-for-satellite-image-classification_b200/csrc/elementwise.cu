@@ -46,6 +46,16 @@ int bn_finalize(const double* stats, int64_t count, const float* gamma, const fl
   return 0;
 }
 
+int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta,
+                  int C, cudaStream_t st);
+
+int run_bn_job(const BnJob& j, cudaStream_t st) {
+  if (j.kind == BN_JOB_FINALIZE)
+    return bn_finalize(j.stats, (int64_t)j.count, j.gamma, j.beta, j.rmean, j.rvar, j.bnc, j.C, j.training, st);
+  if (j.kind == BN_JOB_BWD) return bn_bwd_reduce(j.stats, (int64_t)j.count, j.gamma, j.bnc, j.dgamma, j.dbeta, j.C, st);
+  return 0;
+}
+
 // dy = A*dz + B*(y - mean) + C with  A = gamma*rstd,  B = -A*rstd*S2/M,  C = -A*S1/M
 __global__ void k_bn_bwd_reduce(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                                 float* __restrict__ bnc, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {

@@ -3,7 +3,7 @@
 // stream the caller passes, so whole steps can be captured in a CUDA graph (ae_step_graph_*).
 #include <vector>
 
-#include "common.cuh"
+#include "pack.cuh"
 
 namespace ae {
 
@@ -276,12 +276,36 @@ static int check_part(const ae_engine* e, int p, bool need_grads) {
   return 0;
 }
 
+static BnJob bn_fwd_job(const Part& P, int l, int batch, int training) {
+  const BN& b = P.bn[l];
+  BnJob j{};
+  j.kind = BN_JOB_FINALIZE; j.stats = b.stats_f; j.count = (double)batch * (double)b.count_per_image;
+  j.gamma = P.P(b.gamma); j.beta = P.P(b.beta); j.rmean = P.rmean(l); j.rvar = P.rvar(l); j.bnc = b.bnc;
+  j.dgamma = nullptr; j.dbeta = nullptr; j.C = b.C; j.training = training;
+  return j;
+}
+static BnJob bn_bwd_job(const Part& P, int l, int batch) {
+  const BN& b = P.bn[l];
+  BnJob j{};
+  j.kind = BN_JOB_BWD; j.stats = b.stats_b; j.count = (double)batch * (double)b.count_per_image;
+  j.gamma = P.P(b.gamma); j.beta = nullptr; j.rmean = nullptr; j.rvar = nullptr; j.bnc = b.bnc;
+  j.dgamma = P.G(b.gamma); j.dbeta = P.G(b.beta); j.C = b.C; j.training = 1;
+  return j;
+}
+
 // Row GEMM of a mid layer.  `a` is the fp32 operand description (transform included); on the tcgen05 path its
 // split-bf16 planes are `planes`: produced here when `split_now`, else already current (written earlier this step).
+// `job`: the BatchNorm coefficient job of the operand's layer; it runs inside the split kernel (tcgen05 path) or as its
+// own launch (CUDA-core path).
 static int run_rowgemm(ae_engine* e, RowGemm& r, const Operand& a, void* planes, bool split_now, int64_t a_count,
-                       const void* pk, cudaStream_t st) {
-  if (e->simt) { r.A = a; return simt_rowgemm(r, st); }
-  if (split_now) AE_TRY(tma_split_operand(a, a_count, planes, e->nsplit, st));
+                       const void* pk, const BnJob* job, cudaStream_t st) {
+  if (e->simt) {
+    if (job) AE_TRY(run_bn_job(*job, st));
+    r.A = a;
+    return simt_rowgemm(r, st);
+  }
+  if (split_now) AE_TRY(tma_split_operand(a, a_count, planes, e->nsplit, job, st));
+  else if (job) AE_TRY(run_bn_job(*job, st));
   r.A = split_operand(planes, a.C);
   return tma_rowgemm(r, pk, e->nsplit, st);
 }
@@ -400,6 +424,40 @@ int ae_engine_pack_weights(ae_engine_t* e, int part, ae_stream_t stream) {
   return 0;
 }
 
+// Every weight re-layout of all three parts in ONE launch (tcgen05 path; the captured step uses this after Adam).
+static int pack_all_parts(ae_engine* e, cudaStream_t st) {
+  for (int p = 0; p < AE_NUM_PARTS; ++p) AE_TRY(check_part(e, p, false));
+  const int L = e->L;
+  PackJobs J{};
+  int n = 0;
+  auto conv = [&](const Part& P, MidLayer& m) {
+    PackJob& j = J.job[n++];
+    j.kind = PACK_CONV; j.src = P.P(m.w); j.dst = m.pk_fwd; j.dst2 = m.pk_dgrad;
+    j.a = m.g.Cs; j.b = m.g.Cb; j.c = e->nsplit; j.total = 2 * 9 * m.g.Cs * m.g.Cb;
+  };
+  auto lin = [&](const float* w, int N, int K, int permC, int permHW, int kind, float* dst) {
+    PackJob& j = J.job[n++];
+    j.kind = PACK_LINEAR; j.src = w; j.dst = dst; j.dst2 = nullptr;
+    j.a = N; j.b = K; j.c = permC; j.d = permHW; j.e = kind; j.total = N * K;
+  };
+  const Part& E = e->part[AE_PART_ENC];
+  const Part& D = e->part[AE_PART_DEC];
+  const Part& H = e->part[AE_PART_HEAD];
+  for (int i = 0; i < 3; ++i) { conv(E, e->enc_mid[i]); conv(D, e->dec_mid[i]); }
+  lin(E.P(16), L, 4096, 256, 16, 0, e->encfc_fwd);
+  lin(E.P(16), L, 4096, 256, 16, 1, e->encfc_bwd);
+  lin(D.P(0), 4096, L, 256, 16, 2, e->decfc_fwd);
+  lin(D.P(0), 4096, L, 256, 16, 3, e->decfc_bwd);
+  lin(H.P(0), 128, L, 0, 0, 0, e->head_w1t);
+  {
+    PackJob& j = J.job[n++];
+    j.kind = PACK_PERMUTE; j.src = D.P(1); j.dst = e->decfc_bias; j.dst2 = nullptr;
+    j.a = 4096; j.b = 256; j.c = 16; j.total = 4096;
+  }
+  J.n = n;
+  return pack_all(J, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Encoder (NB:499-525)
 // ---------------------------------------------------------------------------------------------
@@ -418,8 +476,6 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
     Epilogue ep = training ? bias_stats_epilogue(P.P(1), P.bn[0].stats_f, 32) : store_epilogue(P.P(1));
     ep.C = 32;
     AE_TRY(thin_gather_fwd(raw_operand(x), P.P(0), ep, e->y[0], batch, st));
-    AE_TRY(bn_finalize(P.bn[0].stats_f, (int64_t)batch * 1024, P.P(2), P.P(3), P.rmean(0), P.rvar(0), P.bn[0].bnc, 32,
-                       training, st));
   }
   for (int i = 0; i < 3; ++i) {
     MidLayer& m = e->enc_mid[i];
@@ -432,11 +488,11 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
     r.epi = training ? bias_stats_epilogue(P.P(m.b), bout.stats_f, bout.C) : store_epilogue(P.P(m.b));
     r.epi.C = bout.C;
     r.out = e->y[i + 1]; r.splitK = 1; r.partial = nullptr;
+    const BnJob job = bn_fwd_job(P, i, batch, training);      // BatchNorm of this layer's input, finalised in the split
     AE_TRY(run_rowgemm(e, r, bnrelu_operand(e->y[i], bin.bnc, bin.C), e->ae_pl[i], true,
-                       (int64_t)batch * bin.count_per_image * bin.C, m.pk_fwd, st));
-    AE_TRY(bn_finalize(bout.stats_f, (int64_t)batch * bout.count_per_image, P.P(bout.gamma), P.P(bout.beta),
-                       P.rmean(i + 1), P.rvar(i + 1), bout.bnc, bout.C, training, st));
+                       (int64_t)batch * bin.count_per_image * bin.C, m.pk_fwd, &job, st));
   }
+  AE_TRY(run_bn_job(bn_fwd_job(P, 3, batch, training), st));
   {  // Flatten + Linear(4096, L): split-K partials, fixed-order reduce (+bias)
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = e->L; r.K = 4096;
@@ -473,8 +529,6 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     r.epi = relubwd_epilogue(e->y[3], P.bn[3].bnc, P.bn[3].stats_b, 256);
     r.out = e->dzy[3]; r.splitK = 1;
     AE_TRY(simt_rowgemm(r, st));
-    AE_TRY(bn_bwd_reduce(P.bn[3].stats_b, (int64_t)batch * 16, P.P(P.bn[3].gamma), P.bn[3].bnc, P.G(P.bn[3].gamma),
-                         P.G(P.bn[3].beta), 256, st));
   }
   for (int i = 2; i >= 0; --i) {
     MidLayer& m = e->enc_mid[i];
@@ -484,7 +538,9 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     Geom g = m.g; g.B = batch;
     const Operand a_big = bnrelu_operand(e->y[i], bin.bnc, bin.C);                          // planes: ae_pl[i] (forward)
     const Operand dy_small = bnbwd_operand(e->dzy[i + 1], e->y[i + 1], bout.bnc, bout.C);   // planes: dy_pl (now)
-    if (!e->simt) AE_TRY(tma_split_operand(dy_small, (int64_t)Mrows * m.g.Cs, e->dy_pl, e->nsplit, st));
+    const BnJob job = bn_bwd_job(P, i + 1, batch);            // backward coefficients of the output BatchNorm
+    if (!e->simt) AE_TRY(tma_split_operand(dy_small, (int64_t)Mrows * m.g.Cs, e->dy_pl, e->nsplit, &job, st));
+    else AE_TRY(run_bn_job(job, st));
     AE_TRY(run_conv_wgrad(e, g, a_big, dy_small, e->ae_pl[i], e->dy_pl, P.G(m.w), st));
     AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cs * 4, st));   // bias feeding a training BN: exact zero gradient
     RowGemm r{};
@@ -492,10 +548,9 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     r.Bp = (const float*)m.pk_dgrad;
     r.epi = relubwd_epilogue(e->y[i], bin.bnc, bin.stats_b, bin.C);
     r.out = e->dzy[i]; r.splitK = 1;
-    AE_TRY(run_rowgemm(e, r, dy_small, e->dy_pl, false, 0, m.pk_dgrad, st));
-    AE_TRY(bn_bwd_reduce(bin.stats_b, (int64_t)batch * bin.count_per_image, P.P(bin.gamma), bin.bnc, P.G(bin.gamma),
-                         P.G(bin.beta), bin.C, st));
+    AE_TRY(run_rowgemm(e, r, dy_small, e->dy_pl, false, 0, m.pk_dgrad, nullptr, st));
   }
+  AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch), st));
   // conv1 weight gradient (no data gradient needed)
   AE_TRY(thin_wgrad(bnbwd_operand(e->dzy[0], e->y[0], P.bn[0].bnc, 32), raw_operand(e->last_x), P.G(0), nullptr,
                     e->partial, e->partial_bytes, batch, st));
@@ -536,10 +591,12 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
     r.epi = training ? bias_stats_epilogue(P.P(m.b), bout.stats_f, bout.C) : store_epilogue(P.P(m.b));
     r.epi.C = bout.C;
     r.out = e->t[i]; r.splitK = 1;
-    AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], true, (int64_t)r.M * m.g.Cs, m.pk_dgrad, st));
-    AE_TRY(bn_finalize(bout.stats_f, (int64_t)batch * bout.count_per_image, P.P(bout.gamma), P.P(bout.beta), P.rmean(i),
-                       P.rvar(i), bout.bnc, bout.C, training, st));
+    BnJob job{};
+    if (i > 0) job = bn_fwd_job(P, i - 1, batch, training);
+    AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], true, (int64_t)r.M * m.g.Cs, m.pk_dgrad,
+                       i > 0 ? &job : nullptr, st));
   }
+  AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
   float* xo = x_hat ? x_hat : e->xhat;
   AE_TRY(thin_scatter_sigmoid_fwd(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), P.P(14), P.P(15), xo, x_target, e->sse, batch, st));
   if (x_hat && training) AE_CUDA(cudaMemcpyAsync(e->xhat, x_hat, (size_t)batch * 12288 * 4, cudaMemcpyDeviceToDevice, st));
@@ -564,8 +621,6 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
   AE_TRY(thin_bwd_fused(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), thin_up, P.P(14),
                         relubwd_epilogue(e->t[2], P.bn[2].bnc, P.bn[2].stats_b, 32), e->dzt[2], P.G(14), P.G(15), e->partial,
                         e->partial_bytes, batch, st));
-  AE_TRY(bn_bwd_reduce(P.bn[2].stats_b, (int64_t)batch * 1024, P.P(P.bn[2].gamma), P.bn[2].bnc, P.G(P.bn[2].gamma),
-                       P.G(P.bn[2].beta), 32, st));
   for (int i = 2; i >= 0; --i) {
     MidLayer& m = e->dec_mid[i];
     BN& bout = P.bn[i];  // BN after this layer's output (big image)
@@ -574,7 +629,9 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     if (i == 0) small.C = m.g.Cs;                                                   // planes: h_pl / ad_pl[i-1] (forward)
     const Operand dy_big = bnbwd_operand(e->dzt[i], e->t[i], bout.bnc, bout.C);     // planes: dy_pl (now)
     Geom g = m.g; g.B = batch;
-    if (!e->simt) AE_TRY(tma_split_operand(dy_big, (int64_t)Mrows * 4 * m.g.Cb, e->dy_pl, e->nsplit, st));
+    const BnJob job = bn_bwd_job(P, i, batch);
+    if (!e->simt) AE_TRY(tma_split_operand(dy_big, (int64_t)Mrows * 4 * m.g.Cb, e->dy_pl, e->nsplit, &job, st));
+    else AE_TRY(run_bn_job(job, st));
     AE_TRY(run_conv_wgrad(e, g, dy_big, small, e->dy_pl, i == 0 ? e->h_pl : e->ad_pl[i - 1], P.G(m.w), st));
     AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cb * 4, st));
     RowGemm r{};
@@ -583,12 +640,7 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     if (i == 0) { r.epi = store_epilogue(); r.epi.C = m.g.Cs; r.out = e->dh; }
     else { BN& bin = P.bn[i - 1]; r.epi = relubwd_epilogue(e->t[i - 1], bin.bnc, bin.stats_b, bin.C); r.out = e->dzt[i - 1]; }
     r.splitK = 1;
-    AE_TRY(run_rowgemm(e, r, dy_big, e->dy_pl, false, 0, m.pk_fwd, st));
-    if (i > 0) {
-      BN& bin = P.bn[i - 1];
-      AE_TRY(bn_bwd_reduce(bin.stats_b, (int64_t)batch * bin.count_per_image, P.P(bin.gamma), bin.bnc, P.G(bin.gamma),
-                           P.G(bin.beta), bin.C, st));
-    }
+    AE_TRY(run_rowgemm(e, r, dy_big, e->dy_pl, false, 0, m.pk_fwd, nullptr, st));
   }
   {  // decoder_input backward
     ColGemm c{};
@@ -717,7 +769,10 @@ int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels,
   if (rc == 0)
     rc = adam_step_flat(flat_params, flat_grads, adam_m, adam_v, flat_len, adam->lr, adam->beta1, adam->beta2, adam->eps,
                         adam->weight_decay, gscale, step_dev, st);
-  for (int p = 0; rc == 0 && p < AE_NUM_PARTS; ++p) rc = ae_engine_pack_weights(e, p, stream);
+  if (rc == 0) {
+    if (e->simt) { for (int p = 0; rc == 0 && p < AE_NUM_PARTS; ++p) rc = ae_engine_pack_weights(e, p, stream); }
+    else rc = pack_all_parts(e, st);
+  }
   cudaGraph_t graph = nullptr;
   cudaError_t ce = cudaStreamEndCapture(st, &graph);
   if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }

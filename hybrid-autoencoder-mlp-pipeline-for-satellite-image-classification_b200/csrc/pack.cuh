@@ -1,0 +1,91 @@
+// Element-wise weight re-layout routines shared by the stand-alone pack kernels and the fused k_pack_all.
+#pragma once
+#include "common.cuh"
+
+namespace ae {
+
+// One element (idx in [0, 2*9*Cs*Cb)) of the conv weight pack: w [Cs][Cb][3][3] fp32 -> swizzled bf16 (hi[, lo]) tiles
+// for both row-GEMM orientations (layout described in tma_gemm.cu).
+__device__ __forceinline__ void pack_conv_elem(int idx, const float* __restrict__ w, int Cs, int Cb, int nsplit,
+                                               uint8_t* __restrict__ fwd, uint8_t* __restrict__ dgrad) {
+  const int KCf = Cb >= 64 ? 64 : 32, NTf = Cs >= 64 ? 64 : 32;
+  const int NTd = Cb >= 64 ? 64 : 32;
+  const int nf = Cs * 9 * Cb;
+  float v;
+  uint8_t* base;
+  int r, j, NT, KC;
+  size_t tile;
+  if (idx < nf) {
+    const int k = idx % (9 * Cb), n = idx / (9 * Cb);   // n = cs, k = tap*Cb + cb
+    const int tap = k / Cb, cb = k - tap * Cb;
+    v = w[((size_t)n * Cb + cb) * 9 + tap];
+    KC = KCf; NT = NTf;
+    const int kc = k / KC; j = k - kc * KC;
+    r = n % NT; tile = (size_t)(n / NT) * (9 * Cb / KC) + kc; base = fwd;
+  } else {
+    const int i2 = idx - nf;
+    const int k = i2 % (9 * Cs), n = i2 / (9 * Cs);     // n = cb, k = slot*Cs + cs
+    const int slot = k / Cs, cs = k - slot * Cs;        // slot 0: phase 0; 1-2: phase 1; 3-4: phase 2; 5-8: phase 3
+    int ky, kx;
+    if (slot == 0) { ky = 1; kx = 1; }
+    else if (slot <= 2) { ky = 1; kx = slot == 1 ? 0 : 2; }
+    else if (slot <= 4) { ky = slot == 3 ? 0 : 2; kx = 1; }
+    else { const int t = slot - 5; ky = (t >> 1) ? 2 : 0; kx = (t & 1) ? 2 : 0; }
+    v = w[((size_t)cs * Cb + n) * 9 + ky * 3 + kx];
+    KC = 64; NT = NTd;
+    const int kc = k / KC; j = k - kc * KC;
+    r = n % NT; tile = (size_t)(n / NT) * (9 * Cs / KC) + kc; base = dgrad;
+  }
+  const int rowb = KC * 2;
+  const int swz = rowb == 128 ? (r & 7) : ((r >> 1) & 3);
+  const size_t tile_bytes = (size_t)nsplit * NT * rowb;
+  const size_t off = tile * tile_bytes + (size_t)r * rowb + (size_t)((((j >> 3) ^ swz) << 4) + (j & 7) * 2);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+  if (nsplit == 2) *reinterpret_cast<__nv_bfloat16*>(base + off + (size_t)NT * rowb) = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// Linear weight w [N][K] (torch).  perm(k) = (k % permC) * permHW + k / permC maps an NHWC flatten index to the
+// reference's (C,H,W) flatten index (NB:520 / NB:614).
+//  kind 0: dst[k][n]  = w[n][perm(k)]      (K x N, forward of a layer whose INPUT is NHWC-flattened)
+//  kind 1: dst[n][k]  = w[n][perm(k)]      (N x K, its data-gradient operand)
+//  kind 2: dst[k][n'] = w[perm(n')][k]     (K x N, forward of a layer whose OUTPUT is NHWC-flattened)
+//  kind 3: dst[n'][k] = w[perm(n')][k]     (N x K, its data-gradient operand)
+__device__ __forceinline__ void pack_linear_elem(int idx, const float* __restrict__ w, int N, int K, int permC, int permHW,
+                                                 int kind, float* __restrict__ dst) {
+  const int k = idx % K, n = idx / K;  // destination-side logical (n, k)
+  if (kind == 0 || kind == 1) {
+    const int kp = permC > 0 ? (k % permC) * permHW + k / permC : k;
+    const float v = w[(size_t)n * K + kp];
+    if (kind == 0) dst[(size_t)k * N + n] = v; else dst[(size_t)n * K + k] = v;
+  } else {
+    const int np = permC > 0 ? (n % permC) * permHW + n / permC : n;
+    const float v = w[(size_t)np * K + k];
+    if (kind == 2) dst[(size_t)k * N + n] = v; else dst[(size_t)n * K + k] = v;
+  }
+}
+
+__device__ __forceinline__ void permute_elem(int i, const float* __restrict__ src, int permC, int permHW, float* __restrict__ dst) {
+  dst[i] = src[(i % permC) * permHW + i / permC];
+}
+
+// A batch of re-layout jobs executed by ONE launch (k_pack_all): after every optimizer step the engine re-derives
+// the six conv weight packs and the dense-layer packs.
+enum { PACK_CONV = 0, PACK_LINEAR = 1, PACK_PERMUTE = 2 };
+struct PackJob {
+  int kind;
+  const float* src;
+  void* dst;
+  void* dst2;
+  int a, b, c, d, e;        // CONV: Cs, Cb, nsplit.  LINEAR: N, K, permC, permHW, lkind.  PERMUTE: n, permC, permHW
+  int total;                // elements
+  int first_block;          // first block of this job in the fused launch
+};
+static constexpr int PACK_MAX_JOBS = 16;
+struct PackJobs {
+  PackJob job[PACK_MAX_JOBS];
+  int n;
+};
+int pack_all(PackJobs& jobs, cudaStream_t st);
+
+}  // namespace ae

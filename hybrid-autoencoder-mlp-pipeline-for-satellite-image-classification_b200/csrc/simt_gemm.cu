@@ -1,6 +1,6 @@
 // fp32 CUDA-core implicit-GEMM kernels: the bring-up / cross-check backend (AE_BACKEND_SIMT) and the
 // home of the small dense layers.  Same operand-transform and epilogue semantics as the tcgen05 path.
-#include "common.cuh"
+#include "pack.cuh"
 
 namespace ae {
 
@@ -391,28 +391,11 @@ int pack_conv_simt(const float* w, int Cs, int Cb, float* fwd, float* dgrad, cud
   return 0;
 }
 
-// Linear weight w [N][K] (torch).  perm(k) = (k % permC) * permHW + k / permC maps an NHWC flatten index
-// to the reference's (C,H,W) flatten index (NB:520 / NB:614).
-//  kind 0: dst[k][n]  = w[n][perm(k)]      (K x N, forward of a layer whose INPUT is NHWC-flattened)
-//  kind 1: dst[n][k]  = w[n][perm(k)]      (N x K, its data-gradient operand)
-//  kind 2: dst[k][n'] = w[perm(n')][k]     (K x N, forward of a layer whose OUTPUT is NHWC-flattened)
-//  kind 3: dst[n'][k] = w[perm(n')][k]     (N x K, its data-gradient operand)
 __global__ void k_pack_linear(const float* __restrict__ w, int N, int K, int permC, int permHW, int kind,
                               float* __restrict__ dst) {
   const int total = N * K;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    if (kind == 0 || kind == 1) {
-      const int k = idx % K, n = idx / K;  // destination-side logical (n, k)
-      const int kp = permC > 0 ? (k % permC) * permHW + k / permC : k;
-      const float v = w[(size_t)n * K + kp];
-      if (kind == 0) dst[(size_t)k * N + n] = v; else dst[(size_t)n * K + k] = v;
-    } else {
-      const int k = idx % K, n = idx / K;
-      const int np = permC > 0 ? (n % permC) * permHW + n / permC : n;
-      const float v = w[(size_t)np * K + k];
-      if (kind == 2) dst[(size_t)k * N + n] = v; else dst[(size_t)n * K + k] = v;
-    }
-  }
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    pack_linear_elem(idx, w, N, K, permC, permHW, kind, dst);
 }
 
 int pack_linear(const float* w, int N, int K, int permC, int permHW, int kind, float* dst, cudaStream_t st) {
@@ -424,7 +407,7 @@ int pack_linear(const float* w, int N, int K, int permC, int permHW, int kind, f
 
 __global__ void k_permute_vector(const float* __restrict__ src, int n, int permC, int permHW, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[(i % permC) * permHW + i / permC];
+  if (i < n) permute_elem(i, src, permC, permHW, dst);
 }
 
 int permute_vector(const float* src, int n, int permC, int permHW, float* dst, cudaStream_t st) {

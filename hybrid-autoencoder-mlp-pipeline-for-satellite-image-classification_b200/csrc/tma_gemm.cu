@@ -21,6 +21,7 @@
 // AE_PREC_FP32 issues hi*hi + hi*lo + lo*hi (3 MMAs per k-step, fp32 accumulate): ~2^-17 relative error per product.
 #include <mutex>
 
+#include "pack.cuh"
 #include "tc_common.cuh"
 
 namespace ae {
@@ -79,15 +80,76 @@ static void pixel_box(int Hs, int Ws, int rows, int* bx, int* by, int* bn) {
 // ---------------------------------------------------------------------------------------------
 // k_split_operand: fp32 NHWC (+ operand transform) -> split-bf16 planes
 // ---------------------------------------------------------------------------------------------
+// Optionally runs a BatchNorm coefficient job first (every block derives the coefficients of all channels into shared
+// memory from the fp64 sums; block 0 also publishes them and updates the running statistics / parameter gradients),
+// which removes the separate k_bn_finalize / k_bn_bwd_reduce launch in front of it.
 template <int NSPLIT>
 __global__ void __launch_bounds__(256) k_split_operand(Operand op, int64_t n8, int64_t plane_elems,
-                                                      __nv_bfloat16* __restrict__ dst) {
+                                                      __nv_bfloat16* __restrict__ dst, BnJob job) {
+  __shared__ __align__(16) float sc[4][256];             // BNRELU: scale, shift.  BNBWD: A, B, C, mean
+  const int C = op.C;
+  if (op.mode != AE_OP_RAW) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (job.kind == BN_JOB_FINALIZE) {
+        double mean, var;
+        if (job.training) {
+          mean = job.stats[c] / job.count;
+          var = job.stats[C + c] / job.count - mean * mean;
+          if (var < 0.0) var = 0.0;
+        } else {
+          mean = (double)job.rmean[c];
+          var = (double)job.rvar[c];
+        }
+        const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+        const float scale = job.gamma[c] * rstd;
+        const float shift = job.beta[c] - (float)mean * scale;
+        sc[0][c] = scale; sc[1][c] = shift;
+        if (blockIdx.x == 0) {
+          if (job.training && job.rmean) {
+            const double unb = job.count > 1.0 ? var * job.count / (job.count - 1.0) : var;
+            job.rmean[c] = (float)(0.9 * (double)job.rmean[c] + 0.1 * mean);
+            job.rvar[c] = (float)(0.9 * (double)job.rvar[c] + 0.1 * unb);
+          }
+          job.bnc[AE_BNC_SCALE * C + c] = scale; job.bnc[AE_BNC_SHIFT * C + c] = shift;
+          job.bnc[AE_BNC_MEAN * C + c] = (float)mean; job.bnc[AE_BNC_RSTD * C + c] = rstd;
+        }
+      } else if (job.kind == BN_JOB_BWD) {
+        const double s1 = job.stats[c], s2 = job.stats[C + c];
+        const double rstd = (double)job.bnc[AE_BNC_RSTD * C + c];
+        const double a = (double)job.gamma[c] * rstd;
+        const float fa = (float)a, fb = (float)(-a * rstd * s2 / job.count), fk = (float)(-a * s1 / job.count);
+        sc[0][c] = fa; sc[1][c] = fb; sc[2][c] = fk; sc[3][c] = job.bnc[AE_BNC_MEAN * C + c];
+        if (blockIdx.x == 0) {
+          job.bnc[AE_BNC_A * C + c] = fa; job.bnc[AE_BNC_B * C + c] = fb; job.bnc[AE_BNC_C * C + c] = fk;
+          if (job.dgamma) job.dgamma[c] = (float)s2;
+          if (job.dbeta) job.dbeta[c] = (float)s1;
+        }
+      } else if (op.mode == AE_OP_BNRELU) {
+        sc[0][c] = op.bnc[AE_BNC_SCALE * C + c]; sc[1][c] = op.bnc[AE_BNC_SHIFT * C + c];
+      } else {
+        sc[0][c] = op.bnc[AE_BNC_A * C + c]; sc[1][c] = op.bnc[AE_BNC_B * C + c];
+        sc[2][c] = op.bnc[AE_BNC_C * C + c]; sc[3][c] = op.bnc[AE_BNC_MEAN * C + c];
+      }
+    }
+    __syncthreads();
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const size_t off = (size_t)i * 8;
-    const int c = (int)(off % (size_t)op.C);
-    const float4 a = load_operand4(op, off, c, true);
-    const float4 b = load_operand4(op, off + 4, c + 4, true);
-    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int c = (int)(off % (size_t)C);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(op.src + off));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(op.src + off) + 1);
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (op.mode == AE_OP_BNRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[0][c + j], sc[1][c + j]), 0.f);
+    } else if (op.mode == AE_OP_BNBWD) {
+      // dy = A*dz + B*(y - mean) + C, (y - mean) formed first (same order as load_operand4)
+      const float4 y0 = __ldg(reinterpret_cast<const float4*>(op.src2 + off));
+      const float4 y1 = __ldg(reinterpret_cast<const float4*>(op.src2 + off) + 1);
+      const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(sc[0][c + j], v[j], fmaf(sc[1][c + j], y[j] - sc[3][c + j], sc[2][c + j]));
+    }
     uint4 hi;
     hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]); hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
     *reinterpret_cast<uint4*>(dst + off) = hi;
@@ -102,16 +164,25 @@ __global__ void __launch_bounds__(256) k_split_operand(Operand op, int64_t n8, i
   }
 }
 
-int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit, cudaStream_t st) {
+int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit, const BnJob* job, cudaStream_t st) {
   AE_CHECK(count % 8 == 0 && op.C % 8 == 0, "split_operand: count=%lld and C=%d must be multiples of 8", (long long)count, op.C);
   AE_CHECK(op.mode == AE_OP_RAW || op.mode == AE_OP_BNRELU || op.mode == AE_OP_BNBWD, "split_operand: unsupported operand mode %d", op.mode);
+  AE_CHECK(op.mode == AE_OP_RAW || op.C <= 256, "split_operand: at most 256 BatchNorm channels (got %d)", op.C);
   AE_CHECK(((uintptr_t)planes & 15) == 0, "split_operand: destination must be 16-byte aligned");
+  BnJob j;
+  memset(&j, 0, sizeof(j));
+  if (job) {
+    j = *job;
+    AE_CHECK(j.C == op.C && j.bnc == op.bnc, "split_operand: the BatchNorm job must describe the operand's own layer");
+    AE_CHECK((j.kind == BN_JOB_FINALIZE && op.mode == AE_OP_BNRELU) || (j.kind == BN_JOB_BWD && op.mode == AE_OP_BNBWD),
+             "split_operand: BatchNorm job kind %d does not match operand mode %d", j.kind, op.mode);
+  }
   const int64_t n8 = count / 8;
   int64_t blocks = (n8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  if (nsplit == 2) k_split_operand<2><<<(int)blocks, 256, 0, st>>>(op, n8, count, (__nv_bfloat16*)planes);
-  else k_split_operand<1><<<(int)blocks, 256, 0, st>>>(op, n8, count, (__nv_bfloat16*)planes);
+  if (nsplit == 2) k_split_operand<2><<<(int)blocks, 256, 0, st>>>(op, n8, count, (__nv_bfloat16*)planes, j);
+  else k_split_operand<1><<<(int)blocks, 256, 0, st>>>(op, n8, count, (__nv_bfloat16*)planes, j);
   AE_LAUNCH_CHECK();
   return 0;
 }
@@ -362,43 +433,37 @@ static inline int kc_fwd(int Cb) { return Cb >= 64 ? 64 : 32; }
 
 __global__ void k_tma_pack_conv(const float* __restrict__ w, int Cs, int Cb, int nsplit, uint8_t* __restrict__ fwd,
                                 uint8_t* __restrict__ dgrad) {
-  const int KCf = Cb >= 64 ? 64 : 32, NTf = Cs >= 64 ? 64 : 32;
-  const int NTd = Cb >= 64 ? 64 : 32;
-  const int nf = Cs * 9 * Cb, nd = Cb * 9 * Cs;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nf + nd; idx += gridDim.x * blockDim.x) {
-    float v;
-    uint8_t* base;
-    int r, j, NT, KC;
-    size_t tile;
-    if (idx < nf) {
-      const int k = idx % (9 * Cb), n = idx / (9 * Cb);   // n = cs, k = tap*Cb + cb
-      const int tap = k / Cb, cb = k - tap * Cb;
-      v = w[((size_t)n * Cb + cb) * 9 + tap];
-      KC = KCf; NT = NTf;
-      const int kc = k / KC; j = k - kc * KC;
-      r = n % NT; tile = (size_t)(n / NT) * (9 * Cb / KC) + kc; base = fwd;
-    } else {
-      const int i2 = idx - nf;
-      const int k = i2 % (9 * Cs), n = i2 / (9 * Cs);     // n = cb, k = slot*Cs + cs
-      const int slot = k / Cs, cs = k - slot * Cs;        // slot 0: phase 0; 1-2: phase 1; 3-4: phase 2; 5-8: phase 3
-      int ky, kx;
-      if (slot == 0) { ky = 1; kx = 1; }
-      else if (slot <= 2) { ky = 1; kx = slot == 1 ? 0 : 2; }
-      else if (slot <= 4) { ky = slot == 3 ? 0 : 2; kx = 1; }
-      else { const int t = slot - 5; ky = (t >> 1) ? 2 : 0; kx = (t & 1) ? 2 : 0; }
-      v = w[((size_t)cs * Cb + n) * 9 + ky * 3 + kx];
-      KC = 64; NT = NTd;
-      const int kc = k / KC; j = k - kc * KC;
-      r = n % NT; tile = (size_t)(n / NT) * (9 * Cs / KC) + kc; base = dgrad;
-    }
-    const int rowb = KC * 2;
-    const int swz = rowb == 128 ? (r & 7) : ((r >> 1) & 3);
-    const size_t tile_bytes = (size_t)nsplit * NT * rowb;
-    const size_t off = tile * tile_bytes + (size_t)r * rowb + (size_t)((((j >> 3) ^ swz) << 4) + (j & 7) * 2);
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
-    if (nsplit == 2) *reinterpret_cast<__nv_bfloat16*>(base + off + (size_t)NT * rowb) = __float2bfloat16_rn(v - __bfloat162float(hi));
+  const int total = 2 * 9 * Cs * Cb;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    pack_conv_elem(idx, w, Cs, Cb, nsplit, fwd, dgrad);
+}
+
+// Every re-layout job of one optimizer step in a single launch.
+__global__ void __launch_bounds__(256) k_pack_all(const __grid_constant__ PackJobs jobs) {
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].first_block) ++j;
+  const PackJob& J = jobs.job[j];
+  const int nblk = (j + 1 < jobs.n ? jobs.job[j + 1].first_block : (int)gridDim.x) - J.first_block;
+  for (int idx = ((int)blockIdx.x - J.first_block) * blockDim.x + threadIdx.x; idx < J.total; idx += nblk * blockDim.x) {
+    if (J.kind == PACK_CONV) pack_conv_elem(idx, J.src, J.a, J.b, J.c, (uint8_t*)J.dst, (uint8_t*)J.dst2);
+    else if (J.kind == PACK_LINEAR) pack_linear_elem(idx, J.src, J.a, J.b, J.c, J.d, J.e, (float*)J.dst);
+    else permute_elem(idx, J.src, J.b, J.c, (float*)J.dst);
   }
+}
+
+int pack_all(PackJobs& jobs, cudaStream_t st) {
+  AE_CHECK(jobs.n >= 1 && jobs.n <= PACK_MAX_JOBS, "pack_all: %d jobs", jobs.n);
+  int blocks = 0;
+  for (int j = 0; j < jobs.n; ++j) {
+    jobs.job[j].first_block = blocks;
+    int b = (jobs.job[j].total + 255) / 256;
+    if (b > 148) b = 148;
+    if (b < 1) b = 1;
+    blocks += b;
+  }
+  k_pack_all<<<blocks, 256, 0, st>>>(jobs);
+  AE_LAUNCH_CHECK();
+  return 0;
 }
 
 size_t tma_packed_bytes(int Cs, int Cb, int nsplit) { return (size_t)9 * Cs * Cb * 2 * nsplit + 1024; }
