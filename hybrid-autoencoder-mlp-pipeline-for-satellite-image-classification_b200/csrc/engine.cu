@@ -109,7 +109,7 @@ struct ae_engine {
   unsigned int* head_counter = nullptr;
   double* stats_base = nullptr;
   size_t stats_bytes = 0;
-  int fc_split = 16;
+  int fc_split = 64;
   // pointers remembered between forward and backward
   const float* last_x = nullptr;
   const float* last_z_dec = nullptr;

@@ -101,7 +101,26 @@ __global__ void __launch_bounds__(HF_THREADS) k_head_fused(HeadFused a) {
   const int r0 = blockIdx.x * HF_ROWS;
   const int nr = min(HF_ROWS, a.B - r0);
 
-  for (int i = tid; i < HF_H * L; i += HF_THREADS) W1s[(i / L) * LP + (i % L)] = __ldg(a.w1 + i);
+  {  // W1: L is a multiple of 16, so 128-bit loads; all of a thread's loads are issued before the first store
+    const int n4 = HF_H * L / 4;
+    for (int i0 = tid; i0 < n4; i0 += 8 * HF_THREADS) {
+      float4 buf[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * HF_THREADS;
+        buf[u] = i < n4 ? __ldg(reinterpret_cast<const float4*>(a.w1) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * HF_THREADS;
+        if (i < n4) {
+          const int e0 = i * 4, j = e0 / L, k = e0 - j * L;
+          float* d = W1s + j * LP + k;
+          d[0] = buf[u].x; d[1] = buf[u].y; d[2] = buf[u].z; d[3] = buf[u].w;
+        }
+      }
+    }
+  }
   for (int i = tid; i < C * HF_H; i += HF_THREADS) W2s[i] = __ldg(a.w2 + i);
   for (int i = tid; i < HF_ROWS * L; i += HF_THREADS) zs[i] = (i / L) < nr ? __ldg(a.z + (size_t)r0 * L + i) : 0.f;
   __syncthreads();

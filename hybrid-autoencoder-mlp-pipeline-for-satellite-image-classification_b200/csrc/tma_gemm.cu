@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ float sStat[2][NT];
+  __shared__ __align__(16) float sCoef[256][4];             // per output channel: {scale, shift, mean, rstd} or {bias, 0, 0, 0}
 
   const Geom g = q.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -240,6 +241,17 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
     fence_barrier_init();
   }
   if (tid >= 64 && tid < 64 + NT) { sStat[0][tid - 64] = 0.f; sStat[1][tid - 64] = 0.f; }
+  for (int c = tid; c < q.N; c += RG_THREADS) {              // q.N <= 256 output channels
+    float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q.epi.mode == AE_EPI_RELUBWD_STATS) {
+      const int ch = c % q.epi.C;
+      k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
+                      __ldg(q.epi.bnc + AE_BNC_MEAN * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_RSTD * q.epi.C + ch));
+    } else if (q.epi.bias) {
+      k.x = __ldg(q.epi.bias + c);
+    }
+    *reinterpret_cast<float4*>(&sCoef[c][0]) = k;
+  }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -373,17 +385,17 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
             const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int ch = (n + j4 * 4 + j) % e.C;
-              const float z = fmaf(ya[j], __ldg(e.bnc + AE_BNC_SCALE * e.C + ch), __ldg(e.bnc + AE_BNC_SHIFT * e.C + ch));
+              const float4 k = *reinterpret_cast<const float4*>(&sCoef[n + j4 * 4 + j][0]);
+              const float z = fmaf(ya[j], k.x, k.y);
               const float d = (row_ok && z > 0.f) ? v[j4 * 4 + j] : 0.f;
               v[j4 * 4 + j] = d;
-              s2[j4 * 4 + j] = d * ((ya[j] - __ldg(e.bnc + AE_BNC_MEAN * e.C + ch)) * __ldg(e.bnc + AE_BNC_RSTD * e.C + ch));
+              s2[j4 * 4 + j] = d * ((ya[j] - k.z) * k.w);
             }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float d = v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f);
+            float d = v[j] + sCoef[n + j][0];
             d = row_ok ? d : 0.f;
             v[j] = d;
             s2[j] = d * d;
@@ -679,22 +691,44 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_wgrad(const __grid_constant_
   }
 }
 
-// dw[cs][cb][tap] = sum_s partial[s][tap*Cb + cb][cs]   (fixed order -> deterministic)
+// dw[cs][cb][tap] = sum_s partial[s][tap*Cb + cb][cs]   (fixed order -> deterministic).  A block owns 32 float4
+// outputs; its 8 warps each sum every 8th slice (all loads of a thread in flight together), then warp 0 adds the 8
+// shares in order.
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int slices, int I, int J, int Cb,
                                                       float* __restrict__ dw) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int n4 = I * J / 4;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += gridDim.x * blockDim.x) {
-    float4 s = __ldg(reinterpret_cast<const float4*>(partial) + idx);
-    for (int k = 1; k < slices; ++k) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)k * I * J) + idx);
+  const int idx = blockIdx.x * 32 + lane;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < n4) {
+    const size_t stride4 = (size_t)I * J / 4;
+    int k = wq;
+    for (; k + 24 < slices; k += 32) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(partial) + (size_t)k * stride4 + idx);
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(partial) + (size_t)(k + 8) * stride4 + idx);
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(partial) + (size_t)(k + 16) * stride4 + idx);
+      const float4 v3 = __ldg(reinterpret_cast<const float4*>(partial) + (size_t)(k + 24) * stride4 + idx);
+      s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
+      s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; k < slices; k += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + (size_t)k * stride4 + idx);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+  }
+  red[wq][lane] = s;
+  __syncthreads();
+  if (wq == 0 && idx < n4) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) { const float4 v = red[g][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
     const int e = idx * 4;
     const int i = e / J, j = e - i * J;
     const int tap = i / Cb, cb = i - tap * Cb;
     const size_t o = ((size_t)j * Cb + cb) * 9 + tap;
     const size_t js = (size_t)Cb * 9;
-    dw[o] = s.x; dw[o + js] = s.y; dw[o + 2 * js] = s.z; dw[o + 3 * js] = s.w;
+    dw[o] = t.x; dw[o + js] = t.y; dw[o + 2 * js] = t.z; dw[o + 3 * js] = t.w;
   }
 }
 
@@ -758,9 +792,7 @@ int tma_wgrad(const Geom& g, const void* big, const void* small, float* dw, floa
 #undef AE_WG
   AE_TRY(rc);
   const int n4 = q.I * g.Cs / 4;
-  int blocks = (n4 + 255) / 256;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  k_wgrad_reduce<<<blocks, 256, 0, st>>>(partial, slices, q.I, g.Cs, g.Cb, dw);
+  k_wgrad_reduce<<<(n4 + 31) / 32, 256, 0, st>>>(partial, slices, q.I, g.Cs, g.Cb, dw);
   AE_LAUNCH_CHECK();
   return 0;
 }
