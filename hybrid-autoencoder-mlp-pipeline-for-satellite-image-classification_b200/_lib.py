@@ -55,12 +55,13 @@ _SIGS = {
     "ae_conv2d_s2_dgrad": (c_int, [P(ConvGeom), P(Operand), c_void_p, P(Epilogue), c_void_p, c_int, c_int, c_void_p]),
     "ae_conv2d_s2_wgrad_workspace_bytes": (c_size_t, [P(ConvGeom), c_int, c_int]),
     "ae_conv2d_s2_wgrad": (c_int, [P(ConvGeom), P(Operand), P(Operand), c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
-    "ae_thin_gather_fwd": (c_int, [P(Operand), c_void_p, P(Epilogue), c_void_p, c_int, c_void_p]),
-    "ae_thin_scatter_sigmoid_fwd": (c_int, [P(Operand), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "ae_thin_wgrad": (c_int, [P(Operand), P(Operand), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "ae_thin_gather_fwd": (c_int, [P(Operand), c_void_p, P(Epilogue), c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ae_thin_scatter_sigmoid_fwd": (c_int, [P(Operand), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                            c_void_p]),
+    "ae_thin_wgrad": (c_int, [P(Operand), P(Operand), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "ae_thin_wgrad_workspace_bytes": (c_size_t, [c_int]),
     "ae_thin_bwd_fused": (c_int, [P(Operand), P(Operand), c_void_p, P(Epilogue), c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_size_t, c_int, c_void_p]),
+                                  c_size_t, c_int, c_int, c_int, c_void_p]),
     "ae_bn_finalize": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ae_bn_bwd_reduce": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ae_linear_fwd": (c_int, [P(Operand), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -16,6 +16,14 @@ int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias
 size_t thin_wgrad_workspace_bytes(int batch);
 int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
                    float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st);
+int thin_tc_gather_fwd(const Operand& thin, const float* w, const Epilogue& epi, float* out, int batch, int nsplit, cudaStream_t st);
+int thin_tc_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes, int batch,
+                  int nsplit, cudaStream_t st);
+int thin_tc_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
+                      float* dbias, void* partials, size_t bytes, int batch, int nsplit, cudaStream_t st);
+int thin_tc_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* bias, float* x_hat, const float* x,
+                                double* sse, int batch, int nsplit, cudaStream_t st);
+size_t thin_tc_wgrad_workspace_bytes(int batch);
 int bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float* rmean, float* rvar,
                 float* bnc, int C, int training, cudaStream_t st);
 int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta, int C,
@@ -258,6 +266,7 @@ static size_t carve(ae_engine* e, char* base) {
   upd((size_t)colgemm_default_split((int)B, 128, L) * 128 * L * 4);
   upd((size_t)e->fc_split * B * L * 4);
   upd(thin_wgrad_workspace_bytes((int)B));
+  upd(thin_tc_wgrad_workspace_bytes((int)B));
   upd(head_fused_workspace_floats((int)B, L, NC) * 4);
   e->partial_bytes = pb;
   e->partial = (float*)take(pb);
@@ -475,6 +484,8 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
   {
     Epilogue ep = training ? bias_stats_epilogue(P.P(1), P.bn[0].stats_f, 32) : store_epilogue(P.P(1));
     ep.C = 32;
+    // fp32 CUDA cores: the tcgen05 variant (thin_tc_gather_fwd, 27 vs 37 us) puts the 2-term-split error into the very first
+    // layer, which BatchNorm's backward then amplifies; not worth 1 % of the step
     AE_TRY(thin_gather_fwd(raw_operand(x), P.P(0), ep, e->y[0], batch, st));
   }
   for (int i = 0; i < 3; ++i) {
@@ -552,6 +563,7 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
   }
   AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch), st));
   // conv1 weight gradient (no data gradient needed)
+  // (thin_tc_wgrad is parity-green but slower than the CUDA-core kernel: 69 vs 39 us at batch 256, profiles/r1_v4_*)
   AE_TRY(thin_wgrad(bnbwd_operand(e->dzy[0], e->y[0], P.bn[0].bnc, 32), raw_operand(e->last_x), P.G(0), nullptr,
                     e->partial, e->partial_bytes, batch, st));
   AE_CUDA(cudaMemsetAsync(P.G(1), 0, 32 * 4, st));
@@ -598,6 +610,7 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
   }
   AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
   float* xo = x_hat ? x_hat : e->xhat;
+  // (thin_tc_scatter_sigmoid_fwd: same speed as the fp32 CUDA-core kernel, which is the more exact one)
   AE_TRY(thin_scatter_sigmoid_fwd(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), P.P(14), P.P(15), xo, x_target, e->sse, batch, st));
   if (x_hat && training) AE_CUDA(cudaMemcpyAsync(e->xhat, x_hat, (size_t)batch * 12288 * 4, cudaMemcpyDeviceToDevice, st));
   e->last_z_dec = z;
@@ -618,6 +631,7 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
   Part& P = e->part[AE_PART_DEC];
   const int L = e->L;
   // convT4 (32 -> 3)
+  // (thin_tc_bwd_fused: same speed as the fp32 CUDA-core kernel)
   AE_TRY(thin_bwd_fused(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), thin_up, P.P(14),
                         relubwd_epilogue(e->t[2], P.bn[2].bnc, P.bn[2].stats_b, 32), e->dzt[2], P.G(14), P.G(15), e->partial,
                         e->partial_bytes, batch, st));

@@ -140,20 +140,23 @@ int ae_conv2d_s2_wgrad(const ae_conv_geom_t* g, const ae_operand_t* big, const a
  * Thin (3-channel) layers: Conv2d(3,32) NB:504 and ConvTranspose2d(32,3)+Sigmoid NB:628-629.
  * thin = [B,3,64,64] NCHW fp32 (the reference's image layout), wide = [B,32,32,32] NHWC.
  * ---------------------------------------------------------------------------------------- */
+/* backend AE_BACKEND_TC: the threads only build bf16 (hi/lo) operand tiles, tcgen05 does the arithmetic (thin_tc.cu);
+ * AE_BACKEND_SIMT: fp32 CUDA cores (thin.cu).  `precision` as for the GEMM kernels. */
 int ae_thin_gather_fwd(const ae_operand_t* thin, const float* w /*[32,3,3,3]*/, const ae_epilogue_t* epi,
-                       float* out_wide, int batch, ae_stream_t stream);
+                       float* out_wide, int batch, int precision, int backend, ae_stream_t stream);
 /* x_hat = sigmoid(convT(wide) + bias); if x != NULL also accumulates sum((x_hat-x)^2) into *sse (fp64) */
 int ae_thin_scatter_sigmoid_fwd(const ae_operand_t* wide, const float* w /*[32,3,3,3]*/, const float* bias /*[3]*/,
-                                float* x_hat, const float* x, double* sse, int batch, ae_stream_t stream);
+                                float* x_hat, const float* x, double* sse, int batch, int precision, int backend,
+                                ae_stream_t stream);
 int ae_thin_wgrad(const ae_operand_t* wide, const ae_operand_t* thin, float* dw /*[32,3,3,3]*/,
                   float* dbias_thin /*[3] or NULL*/, void* partials, size_t partials_bytes, int batch,
-                  ae_stream_t stream);
+                  int precision, int backend, ae_stream_t stream);
 size_t ae_thin_wgrad_workspace_bytes(int batch);
 /* ae_thin_gather_fwd (data gradient, `epi` = RELUBWD) and ae_thin_wgrad of ConvTranspose2d(32,3) in one pass over the
  * thin operand (autograd of NB:628-629); same workspace as ae_thin_wgrad */
 int ae_thin_bwd_fused(const ae_operand_t* wide, const ae_operand_t* thin, const float* w /*[32,3,3,3]*/,
                       const ae_epilogue_t* epi, float* out_wide, float* dw, float* dbias_thin, void* partials,
-                      size_t partials_bytes, int batch, ae_stream_t stream);
+                      size_t partials_bytes, int batch, int precision, int backend, ae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNorm statistics (NB:505-517, NB:617-625; torch defaults eps 1e-5, momentum 0.1).

@@ -183,7 +183,7 @@ def test_train_step_graph_matches_oracle_over_steps(backend, prec):
             frac, cal = flips / total, flips_cal / total
             print(f"first Adam step {backend}/{prec}: {flips}/{total} entries moved the other way ({frac:.2e}); "
                   f"fp32-vs-fp64 oracle: {cal:.2e}")
-            assert frac <= 3 * cal + (2e-3 if prec == "fp32" else 3e-2), (frac, cal)
+            assert frac <= 3 * cal + (2e-3 if prec == "fp32" else 5e-2), (frac, cal)
 
 
 @pytest.mark.parametrize("backend,prec", CONFIGS)
