@@ -333,12 +333,28 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        # every rank applied the same averaged gradient to the same start weights: the replicas must be bit-identical
+        flat = model.engine().flat.data
+        digest = torch.stack([flat.double().sum(), flat.double().abs().sum()])
+        gathered = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        in_sync = all(torch.equal(g, gathered[0]) for g in gathered)
+        if rank == 0:
+            print(json.dumps({"dp_check": "parameters identical on all ranks after the timed steps", "ok": bool(in_sync),
+                              "world": world}), file=sys.stderr)
+        assert in_sync, "data-parallel replicas diverged"
+        # the captured graph holds NCCL kernels of this communicator: release it before the communicator goes away
+        stepper.close()
+        torch.cuda.synchronize()
         dist.barrier()
         comm.close()
         dist.destroy_process_group()
 
 
 def main():
+    # a hung collective must not hold a multi-GPU box: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("AE_BENCH_WATCHDOG_S", "900")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

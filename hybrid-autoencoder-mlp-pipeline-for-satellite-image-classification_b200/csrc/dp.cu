@@ -60,7 +60,11 @@ int ae_dp_world(const ae_dp_comm_t* c) { return c ? c->world : 1; }
 
 void ae_dp_destroy(ae_dp_comm_t* c) {
   if (!c) return;
-  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm) {
+    // finalize flushes outstanding work; a communicator that cannot be finalised cleanly is aborted rather than left to block exit
+    if (ncclCommFinalize(c->comm) == ncclSuccess) ncclCommDestroy(c->comm);
+    else ncclCommAbort(c->comm);
+  }
   delete c;
 }
 

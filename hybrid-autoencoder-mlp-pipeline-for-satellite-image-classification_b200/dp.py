@@ -39,7 +39,15 @@ def init_communicator() -> Communicator:
     raw = (C.c_uint8 * _lib.DP_UNIQUE_ID_BYTES).from_buffer_copy(obj[0])
     h = C.c_void_p()
     check(lib.ae_dp_init(raw, rank, world, C.byref(h)))
-    return Communicator(h, rank, world)
+    comm = Communicator(h, rank, world)
+    # one eager collective before anything is captured into a CUDA graph: NCCL connects its channels and allocates its
+    # buffers on first use, which is not allowed inside a stream capture
+    warm = torch.ones(1024, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+    comm.allreduce_(warm)
+    torch.cuda.synchronize()
+    if abs(float(warm[0]) - world) > 1e-6:
+        raise RuntimeError(f"ae_b200.dp: warm-up allreduce returned {float(warm[0])}, expected {world}")
+    return comm
 
 
 def shard_bounds(total: int, rank: int, world: int):

@@ -124,10 +124,15 @@ class TrainStep:
         torch.cuda.current_stream(dev).wait_stream(ms)
         return out
 
+    def close(self):
+        """Destroy the captured graph (required before the NCCL communicator it references is destroyed)."""
+        if getattr(self, "handle", None):
+            self.stream.synchronize()
+            _lib.load().ae_step_graph_destroy(self.handle)
+            self.handle = None
+
     def __del__(self):
         try:
-            if getattr(self, "handle", None):
-                _lib.load().ae_step_graph_destroy(self.handle)
-                self.handle = None
+            self.close()
         except Exception:
             pass
