@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_slot;
-  __shared__ float sStat[2][NT];
+  __shared__ float sStat[2][256];                           // per output channel, accumulated over every tile of this CTA
   __shared__ __align__(16) float sCoef[256][4];             // per output channel: {scale, shift, mean, rstd} or {bias, 0, 0, 0}
 
   const Geom g = q.g;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     fence_barrier_init();
   }
-  if (tid >= 64 && tid < 64 + NT) { sStat[0][tid - 64] = 0.f; sStat[1][tid - 64] = 0.f; }
+  for (int c = tid; c < 256; c += RG_THREADS) { sStat[0][c] = 0.f; sStat[1][c] = 0.f; }
   for (int c = tid; c < q.N; c += RG_THREADS) {              // q.N <= 256 output channels
     float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q.epi.mode == AE_EPI_RELUBWD_STATS) {
@@ -409,19 +409,20 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
         if (do_stats) {
           const float a = warp_colsum32_tc(v, lane);
           const float b = warp_colsum32_tc(s2, lane);
-          atomicAdd(&sStat[0][col0 + lane], a);
-          atomicAdd(&sStat[1][col0 + lane], b);
+          atomicAdd(&sStat[0][n + lane], a);
+          atomicAdd(&sStat[1][n + lane], b);
         }
       }
-      if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et < NT) {
-          const int ch = (ntile * NT + et) % e.C;
-          atomicAdd(e.stats + ch, (double)sStat[0][et]);
-          atomicAdd(e.stats + e.C + ch, (double)sStat[1][et]);
-          sStat[0][et] = 0.f; sStat[1][et] = 0.f;
+    }
+    if (do_stats) {                                         // one flush per CTA: fp64 atomics, one per channel
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = et; c < q.N; c += 128) {
+        const float a = sStat[0][c], b = sStat[1][c];
+        if (a != 0.f || b != 0.f) {
+          const int ch = c % e.C;
+          atomicAdd(e.stats + ch, (double)a);
+          atomicAdd(e.stats + e.C + ch, (double)b);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
   }
