@@ -37,7 +37,7 @@ size_t head_fused_workspace_floats(int B, int L, int C);
 int head_fused_step(const float* z, const int64_t* labels, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* logits, float* dz, float* gw1, float* gb1, float* gw2, float* gb2,
                     float* loss, const double* sse, double numel, float alpha, float* partial, unsigned int* counter,
-                    int B, int L, int C, cudaStream_t st);
+                    int B, int L, int C, cudaStream_t st_main, cudaStream_t st_finish, int phase);
 int head_backward_small(const float* dlogits, const float* w2, const float* hid_pre, float* dhid, float* dw2, float* db2,
                         int B, int H, int C, cudaStream_t st);
 
@@ -118,6 +118,16 @@ struct ae_engine {
   double* stats_base = nullptr;
   size_t stats_bytes = 0;
   int fc_split = 64;
+  // second stream of the fused step: independent kernels (a layer's weight gradient next to its data gradient, the
+  // classifier head next to the decoder, the decoder's gradient allreduce next to the encoder backward) become parallel
+  // branches of the captured graph.  Created on first use (the engine can be created without a device for layout queries).
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  float* head_partial = nullptr;      // the head's per-CTA partials (it runs beside kernels that use `partial`)
+  float* partial_side = nullptr;      // split-K partials of the dense weight gradients when they run on the side stream
+  size_t partial_side_bytes = 0;
+  // data-parallel step being captured: gradient exchange interleaved with the backward pass
+  ae_dp_comm_t* step_comm = nullptr;
   // pointers remembered between forward and backward
   const float* last_x = nullptr;
   const float* last_z_dec = nullptr;
@@ -270,8 +280,35 @@ static size_t carve(ae_engine* e, char* base) {
   upd(head_fused_workspace_floats((int)B, L, NC) * 4);
   e->partial_bytes = pb;
   e->partial = (float*)take(pb);
+  e->head_partial = (float*)take(head_fused_workspace_floats((int)B, L, NC) * 4);
+  e->partial_side_bytes = (size_t)colgemm_default_split((int)B, 4096, L) * 4096 * L * 4;
+  e->partial_side = (float*)take(e->partial_side_bytes);
   e->head_counter = (unsigned int*)take(256);
   return off + 256;
+}
+
+static int ensure_side(ae_engine* e) {
+  if (e->side) return 0;
+  AE_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  AE_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  AE_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  AE_CUDA(cudaStreamCreateWithFlags(&e->side2, cudaStreamNonBlocking));
+  AE_CUDA(cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming));
+  AE_CUDA(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
+  return 0;
+}
+// side stream continues from everything issued on `st` so far
+static int fork_side(ae_engine* e, cudaStream_t st) {
+  AE_TRY(ensure_side(e));
+  AE_CUDA(cudaEventRecord(e->ev_fork, st));
+  AE_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  return 0;
+}
+// `st` continues after everything issued on the side stream so far
+static int join_side(ae_engine* e, cudaStream_t st) {
+  AE_CUDA(cudaEventRecord(e->ev_join, e->side));
+  AE_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+  return 0;
 }
 
 static int check_batch(const ae_engine* e, int batch) {
@@ -335,10 +372,10 @@ static int run_conv_wgrad(ae_engine* e, const Geom& g, const Operand& big, const
   return simt_colgemm(c, st);
 }
 
-static int run_wgrad(ae_engine* e, ColGemm& c, cudaStream_t st) {   // dense layers
+static int run_wgrad(ae_engine* e, ColGemm& c, cudaStream_t st, bool side = false) {   // dense layers
   c.splitK = colgemm_default_split(c.M, c.I, c.J);
-  c.partial = e->partial;
-  AE_CHECK((size_t)c.splitK * c.I * c.J * 4 <= e->partial_bytes, "engine: partial buffer too small");
+  c.partial = side ? e->partial_side : e->partial;
+  AE_CHECK((size_t)c.splitK * c.I * c.J * 4 <= (side ? e->partial_side_bytes : e->partial_bytes), "engine: partial buffer too small");
   return simt_colgemm(c, st);
 }
 
@@ -364,7 +401,16 @@ int ae_engine_create(const ae_engine_config_t* cfg, ae_engine_t** out) {
   return 0;
 }
 
-void ae_engine_destroy(ae_engine_t* e) { delete e; }
+void ae_engine_destroy(ae_engine_t* e) {
+  if (!e) return;
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
+  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
+  if (e->side) cudaStreamDestroy(e->side);
+  if (e->side2) cudaStreamDestroy(e->side2);
+  delete e;
+}
 
 int ae_engine_param_layout(const ae_engine_t* e, int part, int64_t* offsets, int64_t* sizes, int64_t* flat_len) {
   if (!e || part < 0 || part >= AE_NUM_PARTS) return -1;
@@ -532,14 +578,17 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     c.A = bnrelu_operand(e->y[3], P.bn[3].bnc, 256);
     c.B = raw_operand(dz);
     c.out = P.G(16); c.permC = 256; c.permHW = 16; c.transposed = 1;
-    AE_TRY(run_wgrad(e, c, st));
-    AE_TRY(column_sums(dz, batch, L, 0, 0, P.G(17), st));
+    const bool par = !e->simt;                         // weight / bias gradient beside the data gradient
+    if (par) AE_TRY(fork_side(e, st));
+    AE_TRY(run_wgrad(e, c, par ? e->side : st, par));
+    AE_TRY(column_sums(dz, batch, L, 0, 0, P.G(17), par ? e->side : st));
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = 4096; r.K = L;
     r.A = raw_operand(dz); r.Bp = e->encfc_bwd;
     r.epi = relubwd_epilogue(e->y[3], P.bn[3].bnc, P.bn[3].stats_b, 256);
     r.out = e->dzy[3]; r.splitK = 1;
     AE_TRY(simt_rowgemm(r, st));
+    if (par) AE_TRY(join_side(e, st));
   }
   for (int i = 2; i >= 0; --i) {
     MidLayer& m = e->enc_mid[i];
@@ -552,7 +601,9 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     const BnJob job = bn_bwd_job(P, i + 1, batch);            // backward coefficients of the output BatchNorm
     if (!e->simt) AE_TRY(tma_split_operand(dy_small, (int64_t)Mrows * m.g.Cs, e->dy_pl, e->nsplit, &job, st));
     else AE_TRY(run_bn_job(job, st));
-    AE_TRY(run_conv_wgrad(e, g, a_big, dy_small, e->ae_pl[i], e->dy_pl, P.G(m.w), st));
+    // the weight gradient runs beside the data gradient (both only read the dy planes)
+    if (!e->simt) AE_TRY(fork_side(e, st));
+    AE_TRY(run_conv_wgrad(e, g, a_big, dy_small, e->ae_pl[i], e->dy_pl, P.G(m.w), e->simt ? st : e->side));
     AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cs * 4, st));   // bias feeding a training BN: exact zero gradient
     RowGemm r{};
     r.family = FAM_DGRAD; r.g = g; r.M = Mrows; r.N = m.g.Cb; r.K = 0;
@@ -560,6 +611,7 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     r.epi = relubwd_epilogue(e->y[i], bin.bnc, bin.stats_b, bin.C);
     r.out = e->dzy[i]; r.splitK = 1;
     AE_TRY(run_rowgemm(e, r, dy_small, e->dy_pl, false, 0, m.pk_dgrad, nullptr, st));
+    if (!e->simt) AE_TRY(join_side(e, st));
   }
   AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch), st));
   // conv1 weight gradient (no data gradient needed)
@@ -646,7 +698,8 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     const BnJob job = bn_bwd_job(P, i, batch);
     if (!e->simt) AE_TRY(tma_split_operand(dy_big, (int64_t)Mrows * 4 * m.g.Cb, e->dy_pl, e->nsplit, &job, st));
     else AE_TRY(run_bn_job(job, st));
-    AE_TRY(run_conv_wgrad(e, g, dy_big, small, e->dy_pl, i == 0 ? e->h_pl : e->ad_pl[i - 1], P.G(m.w), st));
+    if (!e->simt) AE_TRY(fork_side(e, st));
+    AE_TRY(run_conv_wgrad(e, g, dy_big, small, e->dy_pl, i == 0 ? e->h_pl : e->ad_pl[i - 1], P.G(m.w), e->simt ? st : e->side));
     AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cb * 4, st));
     RowGemm r{};
     r.family = FAM_FPROP; r.g = g; r.M = Mrows; r.N = m.g.Cs; r.K = 9 * m.g.Cb;
@@ -655,20 +708,24 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     else { BN& bin = P.bn[i - 1]; r.epi = relubwd_epilogue(e->t[i - 1], bin.bnc, bin.stats_b, bin.C); r.out = e->dzt[i - 1]; }
     r.splitK = 1;
     AE_TRY(run_rowgemm(e, r, dy_big, e->dy_pl, false, 0, m.pk_fwd, nullptr, st));
+    if (!e->simt) AE_TRY(join_side(e, st));
   }
   {  // decoder_input backward
     ColGemm c{};
     c.gather = 0; c.M = batch; c.I = 4096; c.J = L;
     c.A = raw_operand(e->dh); c.B = raw_operand(e->last_z_dec);
     c.out = P.G(0); c.permC = 256; c.permHW = 16; c.transposed = 0;
-    AE_TRY(run_wgrad(e, c, st));
-    AE_TRY(column_sums(e->dh, batch, 4096, 256, 16, P.G(1), st));
+    const bool par = !e->simt;
+    if (par) AE_TRY(fork_side(e, st));
+    AE_TRY(run_wgrad(e, c, par ? e->side : st, par));
+    AE_TRY(column_sums(e->dh, batch, 4096, 256, 16, P.G(1), par ? e->side : st));
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = L; r.K = 4096;
     r.A = raw_operand(e->dh); r.Bp = e->decfc_bwd; r.epi = store_epilogue(); r.out = nullptr;
     r.splitK = e->fc_split; r.partial = e->partial;
     AE_TRY(simt_rowgemm(r, st));
     AE_TRY(reduce_partials(e->partial, e->fc_split, (int64_t)batch * L, nullptr, 0, dz_addend, dz, st));
+    if (par) AE_TRY(join_side(e, st));
   }
   return 0;
 }
@@ -727,19 +784,40 @@ int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int bat
   cudaStream_t st = (cudaStream_t)stream;
   AE_CHECK(e && x && labels && loss_out, "ae_train_step: null argument");
   AE_TRY(ae_encoder_forward(e, x, batch, 1, nullptr, stream));
-  AE_TRY(decoder_forward_impl(e, e->z, batch, 1, nullptr, x, st));
   const double numel = (double)batch * 12288.0;
-  {  // classifier head: forward + cross-entropy + backward + loss assembly in one launch
-    AE_TRY(check_part(e, AE_PART_HEAD, true));
-    Part& H = e->part[AE_PART_HEAD];
-    AE_TRY(head_fused_step(e->z, labels, H.P(0), H.P(1), H.P(2), H.P(3), e->logits, e->dz_head, H.G(0), H.G(1), H.G(2),
-                           H.G(3), loss_out, e->sse, numel, alpha, e->partial, e->head_counter, batch, e->L, e->NC, st));
-  }
+  AE_TRY(check_part(e, AE_PART_HEAD, true));
+  Part& H = e->part[AE_PART_HEAD];
+  // classifier head: forward + cross-entropy + backward in one launch, beside the decoder forward (both only need z);
+  // its reduction also assembles the loss from the decoder's squared error, so it follows the join
+  const bool par = !e->simt;
+  if (par) AE_TRY(fork_side(e, st));
+  AE_TRY(head_fused_step(e->z, labels, H.P(0), H.P(1), H.P(2), H.P(3), e->logits, e->dz_head, H.G(0), H.G(1), H.G(2), H.G(3),
+                         loss_out, e->sse, numel, alpha, e->head_partial, e->head_counter, batch, e->L, e->NC,
+                         par ? e->side : st, st, 1));
+  AE_TRY(decoder_forward_impl(e, e->z, batch, 1, nullptr, x, st));
+  if (par) AE_TRY(join_side(e, st));
+  AE_TRY(head_fused_step(e->z, labels, H.P(0), H.P(1), H.P(2), H.P(3), e->logits, e->dz_head, H.G(0), H.G(1), H.G(2), H.G(3),
+                         loss_out, e->sse, numel, alpha, e->head_partial, e->head_counter, batch, e->L, e->NC, st, st, 2));
   Operand up;
   up.src = x; up.src2 = e->xhat; up.bnc = nullptr; up.scalar = (float)(2.0 * (double)alpha / numel);
   up.mode = AE_OP_SIGMOID_BWD; up.C = 1;
   AE_TRY(decoder_backward_impl(e, up, batch, e->dz_tot, e->dz_head, st));
+  if (e->step_comm) {
+    // data parallel: the decoder's and the head's gradients are complete -- exchange them beside the encoder backward
+    AE_TRY(ensure_side(e));
+    AE_CUDA(cudaEventRecord(e->ev_fork2, st));
+    AE_CUDA(cudaStreamWaitEvent(e->side2, e->ev_fork2, 0));
+    Part& D = e->part[AE_PART_DEC];
+    AE_TRY(ae_dp_allreduce(e->step_comm, D.grads, D.flat_len, e->side2));
+    AE_TRY(ae_dp_allreduce(e->step_comm, H.grads, H.flat_len, e->side2));
+  }
   AE_TRY(ae_encoder_backward(e, e->dz_tot, batch, stream));
+  if (e->step_comm) {
+    Part& E = e->part[AE_PART_ENC];
+    AE_TRY(ae_dp_allreduce(e->step_comm, E.grads, E.flat_len, st));
+    AE_CUDA(cudaEventRecord(e->ev_join2, e->side2));
+    AE_CUDA(cudaStreamWaitEvent(st, e->ev_join2, 0));
+  }
   return 0;
 }
 
@@ -774,12 +852,14 @@ int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels,
   AE_CHECK(e && out && adam, "ae_step_graph_capture: null argument");
   AE_CHECK(st != nullptr, "ae_step_graph_capture: needs a non-default stream");
   AE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  // with a communicator the step exchanges its gradients itself (three sum-allreduces that together cover the flat
+  // gradient buffer, the first two overlapped with the encoder backward)
+  e->step_comm = comm;
   int rc = ae_train_step(e, x, labels, batch, alpha, loss_out, stream);
+  e->step_comm = nullptr;
+  (void)flat_grads;
   float gscale = 1.f;
-  if (rc == 0 && comm) {
-    rc = ae_dp_allreduce(comm, flat_grads, flat_len, stream);
-    gscale = 1.f / (float)ae_dp_world(comm);
-  }
+  if (rc == 0 && comm) gscale = 1.f / (float)ae_dp_world(comm);
   if (rc == 0)
     rc = adam_step_flat(flat_params, flat_grads, adam_m, adam_v, flat_len, adam->lr, adam->beta1, adam->beta2, adam->eps,
                         adam->weight_decay, gscale, step_dev, st);

@@ -249,28 +249,34 @@ size_t head_fused_workspace_floats(int B, int L, int C) {
   return (size_t)ctas * (HF_H * L + HF_H + C * HF_H + C + 1);
 }
 
+// `st_main` launches the per-row kernel; `st_finish` (may be the same stream) launches the reduction that also reads
+// the decoder's squared-error sum -- the caller orders st_finish after st_main and after the decoder forward.
 int head_fused_step(const float* z, const int64_t* labels, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* logits, float* dz, float* gw1, float* gb1, float* gw2, float* gb2,
                     float* loss, const double* sse, double numel, float alpha, float* partial, unsigned int* counter,
-                    int B, int L, int C, cudaStream_t st) {
+                    int B, int L, int C, cudaStream_t st_main, cudaStream_t st_finish, int phase) {
   AE_CHECK(C <= 16 && L <= 256, "head_fused_step: num_classes=%d (max 16) / latent_dim=%d (max 256) out of range", C, L);
   HeadFused a;
   a.z = z; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.labels = labels; a.logits = logits; a.dz = dz; a.loss = loss;
   a.gw1 = gw1; a.gb1 = gb1; a.gw2 = gw2; a.gb2 = gb2; a.partial = partial; a.counter = counter; a.sse = sse;
   a.numel = numel; a.alpha = alpha; a.B = B; a.L = L; a.C = C;
-  const size_t smem = sizeof(float) * ((size_t)HF_H * (L + 1) + (size_t)C * HF_H + (size_t)HF_ROWS * L +
-                                       2 * (size_t)HF_ROWS * HF_H + HF_ROWS * 16 + HF_ROWS);
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) {
-    AE_CUDA(cudaFuncSetAttribute(k_head_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
   const int ctas = (B + HF_ROWS - 1) / HF_ROWS;
-  k_head_fused<<<ctas, HF_THREADS, smem, st>>>(a);
-  AE_LAUNCH_CHECK();
-  const int psize = HF_H * L + HF_H + C * HF_H + C + 1;
-  k_head_reduce<<<(psize + 255) / 256, 256, 0, st>>>(a, ctas);
-  AE_LAUNCH_CHECK();
+  if (phase == 0 || phase == 1) {
+    const size_t smem = sizeof(float) * ((size_t)HF_H * (L + 1) + (size_t)C * HF_H + (size_t)HF_ROWS * L +
+                                         2 * (size_t)HF_ROWS * HF_H + HF_ROWS * 16 + HF_ROWS);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+      AE_CUDA(cudaFuncSetAttribute(k_head_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
+    k_head_fused<<<ctas, HF_THREADS, smem, st_main>>>(a);
+    AE_LAUNCH_CHECK();
+  }
+  if (phase == 0 || phase == 2) {
+    const int psize = HF_H * L + HF_H + C * HF_H + C + 1;
+    k_head_reduce<<<(psize + 255) / 256, 256, 0, st_finish>>>(a, ctas);
+    AE_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -81,7 +81,7 @@ def test_ae_dropin_training_loop_golden(tag, backend, prec):
         if s == 0:
             for k, gr in grads.items():
                 # max-norm on sampled entries: bounded loosely (single ReLU-branch flips move single entries)
-                rt, at = gu_gold.grad_tolerances(k, max(2e-2, 3 * gu.GRAD_TOL[(backend, prec)]), 1.0)
+                rt, at = gu_gold.grad_tolerances(k, max(2e-2, 5 * gu.GRAD_TOL[(backend, prec)]), 1.0)
                 gu_gold.check(g, f"s{s}/grad/{k}", gr.cpu().numpy(), rt, atol=at)
             for k, v in model.state_dict().items():
                 if k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"):
@@ -130,7 +130,7 @@ def test_ae_fused_train_step_vs_oracle(batch, backend, prec):
         if r > worst[1]:
             worst = (k, r)
         if batch > 1:
-            assert gu.rel(p.grad, grads[k]) <= max(2e-2, 3 * gu.GRAD_TOL[(backend, prec)]), k
+            assert gu.rel(p.grad, grads[k]) <= max(2e-2, 5 * gu.GRAD_TOL[(backend, prec)]), k
     print(f"batch {batch} {backend}/{prec}: worst gradient rel-L2 vs fp64 oracle: ours {worst[1]:.2e} ({worst[0]}), fp32 CPU reference {worst32:.2e}")
     if batch > 1:      # batch 1: BatchNorm over 16..1024 pixels of one image only -- degenerate conditioning
         # calibrated by the reference arithmetic itself: the fp32 CPU oracle is `worst32` away from the fp64 one
