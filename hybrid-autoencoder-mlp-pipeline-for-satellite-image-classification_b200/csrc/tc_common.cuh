@@ -101,6 +101,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 256-bit store: one full 32-byte sector per thread, so the L2 never has to fill a partially written sector from DRAM
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[32], int j8) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "f"(v[j8 * 8 + 0]), "f"(v[j8 * 8 + 1]), "f"(v[j8 * 8 + 2]), "f"(v[j8 * 8 + 3]), "f"(v[j8 * 8 + 4]),
+                 "f"(v[j8 * 8 + 5]), "f"(v[j8 * 8 + 6]), "f"(v[j8 * 8 + 7])
+               : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory matrix descriptor.  `row_bytes` is the swizzle span: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B);
 // rows are `row_bytes` apart, 8-row groups are `sbo` bytes apart.

@@ -205,8 +205,7 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin(Operand thin, Operand wide,
         }
       }
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4)
-        reinterpret_cast<float4*>(out + row)[q4] = make_float4(acc[q4 * 4], acc[q4 * 4 + 1], acc[q4 * 4 + 2], acc[q4 * 4 + 3]);
+      for (int j8 = 0; j8 < 4; ++j8) st_global_v8(out + row + j8 * 8, acc, j8);   // full 32-byte sectors
       if (e.mode != AE_EPI_STORE && e.stats) {
         st1 += warp_colsum32(acc, lane);
         st2 += warp_colsum32(s2v, lane);

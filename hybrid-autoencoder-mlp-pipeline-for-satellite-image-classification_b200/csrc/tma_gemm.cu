@@ -403,8 +403,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
         }
         if (row_ok) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            reinterpret_cast<float4*>(q.out + orow + n)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+          for (int j8 = 0; j8 < 4; ++j8) st_global_v8(q.out + orow + n + j8 * 8, v, j8);
         }
         if (do_stats) {
           const float a = warp_colsum32_tc(v, lane);
@@ -675,8 +674,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_wgrad(const __grid_constant_
         tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
         if (i < q.I) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            reinterpret_cast<float4*>(dst + col0)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+          for (int j8 = 0; j8 < 4; ++j8) st_global_v8(dst + col0 + j8 * 8, v, j8);
         }
       }
     } else if (i < q.I) {
