@@ -182,7 +182,7 @@ int sigmoid_mse(const float* x_hat, const float* x, int64_t n, float scale, floa
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, int64_t n4, float lr, float b1, float b2, float eps,
-                                              float wd, float gscale, int* __restrict__ step) {
+                                              float wd, float gscale, int* __restrict__ step, int bump) {
   const int t = step[0] + 1;
   const double bc1 = 1.0 - pow((double)b1, (double)t);
   const double bc2 = 1.0 - pow((double)b2, (double)t);
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
     reinterpret_cast<float4*>(v)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (bump && threadIdx.x == 0) {
     __threadfence();
     const int done = atomicAdd(&step[1], 1);
     if (done == (int)gridDim.x - 1) {
@@ -221,6 +221,20 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   }
 }
 
+// bump == 0: apply step number step[0]+1 without advancing the counter (a flat buffer updated by several launches)
+int adam_step_flat_range(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                         float wd, float gscale, int* step_dev, int bump, cudaStream_t st) {
+  AE_CHECK(n % 4 == 0, "adam_step_flat: n=%lld must be a multiple of 4 (pad the flat buffer)", (long long)n);
+  AE_CHECK((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step_flat: buffers must be 16-byte aligned");
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  k_adam<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n4, lr, b1, b2, eps, wd, gscale, step_dev, bump);
+  AE_LAUNCH_CHECK();
+  return 0;
+}
+
 int adam_step_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                    float wd, float gscale, int* step_dev, cudaStream_t st) {
   AE_CHECK(n % 4 == 0, "adam_step_flat: n=%lld must be a multiple of 4 (pad the flat buffer)", (long long)n);
@@ -229,7 +243,7 @@ int adam_step_flat(float* p, const float* g, float* m, float* v, int64_t n, floa
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  k_adam<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n4, lr, b1, b2, eps, wd, gscale, step_dev);
+  k_adam<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n4, lr, b1, b2, eps, wd, gscale, step_dev, 1);
   AE_LAUNCH_CHECK();
   return 0;
 }

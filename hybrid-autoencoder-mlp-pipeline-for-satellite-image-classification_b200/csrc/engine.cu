@@ -32,6 +32,8 @@ int softmax_ce(const float* logits, const int64_t* labels, int B, int C, float g
                int* correct, const double* sse, double numel, float alpha, cudaStream_t st);
 int adam_step_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                    float wd, float gscale, int* step_dev, cudaStream_t st);
+int adam_step_flat_range(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                         float wd, float gscale, int* step_dev, int bump, cudaStream_t st);
 int head_out(const float* hid_pre, const float* w2, const float* b2, float* logits, int B, int H, int C, cudaStream_t st);
 size_t head_fused_workspace_floats(int B, int L, int C);
 int head_fused_step(const float* z, const int64_t* labels, const float* w1, const float* b1, const float* w2,
@@ -128,6 +130,7 @@ struct ae_engine {
   size_t partial_side_bytes = 0;
   // data-parallel step being captured: gradient exchange interleaved with the backward pass
   ae_dp_comm_t* step_comm = nullptr;
+  bool defer_conv1_wgrad = false;     // the captured step runs conv1's weight gradient beside Adam + re-pack of everything else
   // pointers remembered between forward and backward
   const float* last_x = nullptr;
   const float* last_z_dec = nullptr;
@@ -565,6 +568,13 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
   return 0;
 }
 
+// conv1 weight gradient (no data gradient needed): the last piece of the encoder backward
+static int conv1_wgrad(ae_engine* e, int batch, cudaStream_t st) {
+  Part& P = e->part[AE_PART_ENC];
+  return thin_wgrad(bnbwd_operand(e->dzy[0], e->y[0], P.bn[0].bnc, 32), raw_operand(e->last_x), P.G(0), nullptr, e->partial,
+                    e->partial_bytes, batch, st);
+}
+
 int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   AE_TRY(check_batch(e, batch));
@@ -614,11 +624,8 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     if (!e->simt) AE_TRY(join_side(e, st));
   }
   AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch), st));
-  // conv1 weight gradient (no data gradient needed)
-  // (thin_tc_wgrad is parity-green but slower than the CUDA-core kernel: 69 vs 39 us at batch 256, profiles/r1_v4_*)
-  AE_TRY(thin_wgrad(bnbwd_operand(e->dzy[0], e->y[0], P.bn[0].bnc, 32), raw_operand(e->last_x), P.G(0), nullptr,
-                    e->partial, e->partial_bytes, batch, st));
   AE_CUDA(cudaMemsetAsync(P.G(1), 0, 32 * 4, st));
+  if (!e->defer_conv1_wgrad) AE_TRY(conv1_wgrad(e, batch, st));
   return 0;
 }
 
@@ -855,17 +862,35 @@ int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels,
   // with a communicator the step exchanges its gradients itself (three sum-allreduces that together cover the flat
   // gradient buffer, the first two overlapped with the encoder backward)
   e->step_comm = comm;
+  // Single GPU, tcgen05 path: conv1's weight gradient (the last 40 us of the backward pass, and the only gradient still
+  // missing) runs beside Adam + weight re-pack of every other parameter; its own 864 weights are updated after the join.
+  const int64_t c1 = 864;   // conv1.weight = the first tensor of the encoder part
+  const bool split_tail = !comm && !e->simt && e->part[AE_PART_ENC].params == flat_params && flat_len > c1;
+  e->defer_conv1_wgrad = split_tail;
   int rc = ae_train_step(e, x, labels, batch, alpha, loss_out, stream);
   e->step_comm = nullptr;
-  (void)flat_grads;
+  e->defer_conv1_wgrad = false;
   float gscale = 1.f;
   if (rc == 0 && comm) gscale = 1.f / (float)ae_dp_world(comm);
-  if (rc == 0)
-    rc = adam_step_flat(flat_params, flat_grads, adam_m, adam_v, flat_len, adam->lr, adam->beta1, adam->beta2, adam->eps,
-                        adam->weight_decay, gscale, step_dev, st);
-  if (rc == 0) {
-    if (e->simt) { for (int p = 0; rc == 0 && p < AE_NUM_PARTS; ++p) rc = ae_engine_pack_weights(e, p, stream); }
-    else rc = pack_all_parts(e, st);
+  if (rc == 0 && split_tail) {
+    rc = fork_side(e, st);
+    if (rc == 0) rc = conv1_wgrad(e, batch, e->side);
+    if (rc == 0)
+      rc = adam_step_flat_range(flat_params + c1, flat_grads + c1, adam_m + c1, adam_v + c1, flat_len - c1, adam->lr, adam->beta1,
+                                adam->beta2, adam->eps, adam->weight_decay, gscale, step_dev, 0, st);
+    if (rc == 0) rc = pack_all_parts(e, st);
+    if (rc == 0) rc = join_side(e, st);
+    if (rc == 0)
+      rc = adam_step_flat_range(flat_params, flat_grads, adam_m, adam_v, c1, adam->lr, adam->beta1, adam->beta2, adam->eps,
+                                adam->weight_decay, gscale, step_dev, 1, st);
+  } else {
+    if (rc == 0)
+      rc = adam_step_flat(flat_params, flat_grads, adam_m, adam_v, flat_len, adam->lr, adam->beta1, adam->beta2, adam->eps,
+                          adam->weight_decay, gscale, step_dev, st);
+    if (rc == 0) {
+      if (e->simt) { for (int p = 0; rc == 0 && p < AE_NUM_PARTS; ++p) rc = ae_engine_pack_weights(e, p, stream); }
+      else rc = pack_all_parts(e, st);
+    }
   }
   cudaGraph_t graph = nullptr;
   cudaError_t ce = cudaStreamEndCapture(st, &graph);
