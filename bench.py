@@ -141,7 +141,10 @@ def run_reference(args):
 # rotating over more buffers than fit in L2.  Algorithmic bytes per launch: the operand
 # planes once + the packed weights once + the fp32 output once.
 # --------------------------------------------------------------------------------------------------
-TRAFFIC_NCU = {"fp32": 27.3e6, "bf16": None}    # dram__bytes_read+write per launch, profiles/r1_rowgemm_dgrad64_full.txt
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1_v6_roofline_kernel_full.txt (ncu --set full of this
+# very loop): 8.73 MB read = the operand planes + weights, exactly the algorithmic reads; 0 written inside the kernel's window
+# (the 16.8 MB output is still dirty in the 126 MB L2 when the kernel ends)
+TRAFFIC_NCU = {"fp32": 8.73e6, "bf16": None}
 
 
 def kernel_roofline(dev, B, precision, iters=60):
@@ -259,10 +262,10 @@ def run_ours(args):
             stepper.run()
 
     # ---- device-resident throughput ----
-    device_steps(args.warmup)
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    device_steps(args.warmup)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
