@@ -196,26 +196,43 @@ def kernel_roofline(dev, B, precision, iters=60):
             "peak_source": peaks["source"], "l2": f"inputs/outputs rotate over {n_rot} buffer sets ({n_rot * (a_bytes + o_bytes) / 1e6:.0f} MB > L2)"}
 
 
-def inference_rate(dev, precision, backend, batch=4096, iters=20):
+FLOP_PER_IMAGE_INFER = 30.64e6   # encoder + MLP forward
+
+
+def inference_rate(dev, precision, backend, batch=4096, iters=20, sweep=(1024, 4096, 16384, 65536)):
     """BASELINE's second metric: encoder + MLP inference images/s (clf(enc(x)).argmax(1), eval mode), device-resident
-    inputs rotating over > L2, CUDA events."""
+    inputs rotating over > L2, CUDA events.  `sweep`: BASELINE configs[4] (batch 1k-64k), the same measurement per batch
+    size (batches above AE_B200_EVAL_CHUNK are walked in chunks by the encoder shell)."""
     import ae_b200
     torch.manual_seed(1)
     ae = ae_b200.SupervisedAutoencoder(64, 10, precision=precision, backend=backend).to(dev).eval()
     clf = ae_b200.MLP(64, 10).to(dev).eval()
-    xs = [torch.rand(batch, 3, 64, 64, device=dev) for _ in range(3)]     # 3 x 201 MB
-    for i in range(3):
-        ae_b200.encode_predict(ae.enc, clf, xs[i % 3])
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        ae_b200.encode_predict(ae.enc, clf, xs[i % 3])
-    e1.record()
-    torch.cuda.synchronize()
-    t = e0.elapsed_time(e1) * 1e-3 / iters
-    return {"metric": "encoder+MLP infer img/s", "value": batch / t, "unit": "images/s", "batch": batch, "ms_per_batch": t * 1e3,
-            "dtype": precision}
+    peaks = measured_peaks()
+
+    def rate(b, n_it):
+        n_in = max(2, min(3, int(260e6 // (b * 49152)) + 1))          # > 2 x L2 of distinct input bytes in rotation
+        xs = [torch.rand(b, 3, 64, 64, device=dev) for _ in range(n_in)]
+        for i in range(3):
+            ae_b200.encode_predict(ae.enc, clf, xs[i % n_in])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_it):
+            ae_b200.encode_predict(ae.enc, clf, xs[i % n_in])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / n_it
+
+    t = rate(batch, iters)
+    out = {"metric": "encoder+MLP infer img/s", "value": batch / t, "unit": "images/s", "batch": batch, "ms_per_batch": t * 1e3,
+           "dtype": precision, "tflops": batch / t * FLOP_PER_IMAGE_INFER / 1e12,
+           "input_gbs": batch / t * 49152 / 1e9, "frac_of_hbm_input_bound": batch / t * 49152 / 1e9 / peaks["hbm"]}
+    if sweep:
+        out["sweep"] = []
+        for b in sweep:
+            tb = rate(b, max(3, min(iters, int(200000 // b) + 1)))
+            out["sweep"].append({"batch": b, "images_per_s": b / tb, "ms_per_batch": tb * 1e3})
+    return out
 
 
 # --------------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libae_b200.so")
 PREC_FP32, PREC_BF16 = 0, 1
 BACKEND_TC, BACKEND_SIMT = 0, 1
 OP_RAW, OP_BNRELU, OP_BNBWD, OP_SIGMOID_BWD, OP_SPLIT_BF16 = 0, 1, 2, 3, 4
-EPI_STORE, EPI_BIAS_STATS, EPI_RELUBWD_STATS = 0, 1, 2
+EPI_STORE, EPI_BIAS_STATS, EPI_RELUBWD_STATS, EPI_BNRELU_SPLIT = 0, 1, 2, 3
 PART_ENC, PART_DEC, PART_HEAD = 0, 1, 2
 BNC_ROWS = 8
 DP_UNIQUE_ID_BYTES = 128

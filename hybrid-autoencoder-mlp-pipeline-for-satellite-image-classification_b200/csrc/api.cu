@@ -154,7 +154,9 @@ int ae_thin_gather_fwd(const ae_operand_t* thin, const float* w, const ae_epilog
   AE_CHECK(thin && w && out_wide && batch >= 1, "ae_thin_gather_fwd: bad argument");
   if (backend == AE_BACKEND_TC)
     return thin_tc_gather_fwd(make_operand(thin, 3), w, make_epilogue(epi, 32), out_wide, batch, nsplit_of(precision), (cudaStream_t)stream);
-  return thin_gather_fwd(make_operand(thin, 3), w, make_epilogue(epi, 32), out_wide, batch, (cudaStream_t)stream);
+  Epilogue ep = make_epilogue(epi, 32);
+  ep.nsplit = nsplit_of(precision);                   // AE_EPI_BNRELU_SPLIT: planes written
+  return thin_gather_fwd(make_operand(thin, 3), w, ep, out_wide, batch, (cudaStream_t)stream);
 }
 
 int ae_thin_scatter_sigmoid_fwd(const ae_operand_t* wide, const float* w, const float* bias, float* x_hat, const float* x,

@@ -529,13 +529,20 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
     AE_CUDA(cudaMemsetAsync(P.bn[0].stats_f, 0, (char*)(P.bn[3].stats_b + 2 * P.bn[3].C) - (char*)P.bn[0].stats_f, st));
     if (P.steps) { k_inc_i64<<<1, 32, 0, st>>>(P.steps, 4); AE_LAUNCH_CHECK(); }
   }
+  // Eval mode on the tcgen05 path: the BatchNorm coefficients come from the running statistics, so they are known before
+  // the first kernel runs and every layer's epilogue can emit the next layer's operand directly -- split-bf16 planes of
+  // relu(bn(conv + bias)) -- instead of an fp32 tensor that a second pass would normalise and split.
+  const bool fused_eval = !training && !e->simt;
+  if (fused_eval)
+    for (int l = 0; l < 4; ++l) AE_TRY(run_bn_job(bn_fwd_job(P, l, batch, 0), st));
   // conv1 (3 -> 32): x NCHW fp32 -> y1 NHWC
   {
-    Epilogue ep = training ? bias_stats_epilogue(P.P(1), P.bn[0].stats_f, 32) : store_epilogue(P.P(1));
+    Epilogue ep = training ? bias_stats_epilogue(P.P(1), P.bn[0].stats_f, 32)
+                           : fused_eval ? bnrelu_split_epilogue(P.P(1), P.bn[0].bnc, 32, e->nsplit) : store_epilogue(P.P(1));
     ep.C = 32;
     // fp32 CUDA cores: the tcgen05 variant (thin_tc_gather_fwd, 27 vs 37 us) puts the 2-term-split error into the very first
     // layer, which BatchNorm's backward then amplifies; not worth 1 % of the step
-    AE_TRY(thin_gather_fwd(raw_operand(x), P.P(0), ep, e->y[0], batch, st));
+    AE_TRY(thin_gather_fwd(raw_operand(x), P.P(0), ep, fused_eval ? (float*)e->ae_pl[0] : e->y[0], batch, st));
   }
   for (int i = 0; i < 3; ++i) {
     MidLayer& m = e->enc_mid[i];
@@ -548,11 +555,19 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
     r.epi = training ? bias_stats_epilogue(P.P(m.b), bout.stats_f, bout.C) : store_epilogue(P.P(m.b));
     r.epi.C = bout.C;
     r.out = e->y[i + 1]; r.splitK = 1; r.partial = nullptr;
+    if (fused_eval) {
+      // the operand planes were written by the previous layer's epilogue; conv2 / conv3 write the next ones, conv4 stores
+      // fp32 for the dense layer (which applies BatchNorm + ReLU while it loads)
+      if (i < 2) { r.epi = bnrelu_split_epilogue(P.P(m.b), bout.bnc, bout.C, e->nsplit); r.out = (float*)e->ae_pl[i + 1]; }
+      r.A = split_operand(e->ae_pl[i], bin.C);
+      AE_TRY(tma_rowgemm(r, m.pk_fwd, e->nsplit, st));
+      continue;
+    }
     const BnJob job = bn_fwd_job(P, i, batch, training);      // BatchNorm of this layer's input, finalised in the split
     AE_TRY(run_rowgemm(e, r, bnrelu_operand(e->y[i], bin.bnc, bin.C), e->ae_pl[i], true,
                        (int64_t)batch * bin.count_per_image * bin.C, m.pk_fwd, &job, st));
   }
-  AE_TRY(run_bn_job(bn_fwd_job(P, 3, batch, training), st));
+  if (!fused_eval) AE_TRY(run_bn_job(bn_fwd_job(P, 3, batch, training), st));
   {  // Flatten + Linear(4096, L): split-K partials, fixed-order reduce (+bias)
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = e->L; r.K = 4096;
@@ -644,6 +659,9 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
   } else {
     AE_CUDA(cudaMemsetAsync(e->sse, 0, 16, st));
   }
+  const bool fused_eval = !training && !e->simt;        // see ae_encoder_forward
+  if (fused_eval)
+    for (int l = 0; l < 3; ++l) AE_TRY(run_bn_job(bn_fwd_job(P, l, batch, 0), st));
   {  // decoder_input: Linear(L, 4096) + Unflatten, written NHWC
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = 4096; r.K = e->L;
@@ -662,12 +680,20 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
     r.epi = training ? bias_stats_epilogue(P.P(m.b), bout.stats_f, bout.C) : store_epilogue(P.P(m.b));
     r.epi.C = bout.C;
     r.out = e->t[i]; r.splitK = 1;
+    if (fused_eval) {
+      // convT1 / convT2 emit the next layer's operand planes; convT3 stores fp32 for the 3-channel scatter kernel
+      if (i == 0) AE_TRY(tma_split_operand(a, (int64_t)r.M * m.g.Cs, e->h_pl, e->nsplit, nullptr, st));
+      if (i < 2) { r.epi = bnrelu_split_epilogue(P.P(m.b), bout.bnc, bout.C, e->nsplit); r.out = (float*)e->ad_pl[i]; }
+      r.A = split_operand(i == 0 ? e->h_pl : e->ad_pl[i - 1], m.g.Cs);
+      AE_TRY(tma_rowgemm(r, m.pk_dgrad, e->nsplit, st));
+      continue;
+    }
     BnJob job{};
     if (i > 0) job = bn_fwd_job(P, i - 1, batch, training);
     AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], true, (int64_t)r.M * m.g.Cs, m.pk_dgrad,
                        i > 0 ? &job : nullptr, st));
   }
-  AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
+  if (!fused_eval) AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
   float* xo = x_hat ? x_hat : e->xhat;
   // (thin_tc_scatter_sigmoid_fwd: same speed as the fp32 CUDA-core kernel, which is the more exact one)
   AE_TRY(thin_scatter_sigmoid_fwd(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), P.P(14), P.P(15), xo, x_target, e->sse, batch, st));

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) k_rowgemm(RowGemm p) {
 
 int simt_rowgemm(const RowGemm& p, cudaStream_t st) {
   AE_CHECK(p.N % 4 == 0, "simt_rowgemm: N=%d must be a multiple of 4", p.N);
+  AE_CHECK(p.epi.mode != AE_EPI_BNRELU_SPLIT, "simt_rowgemm: the split-bf16 epilogue exists on the tcgen05 path only");
   dim3 grid((p.M + 63) / 64, (p.N + 63) / 64, 1);
   if (p.family == FAM_DGRAD) {
     AE_CHECK(p.g.Cs % 16 == 0, "simt_rowgemm: Cs=%d must be a multiple of 16", p.g.Cs);
@@ -321,9 +322,55 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int splits,
   }
 }
 
+// Many splits, few outputs (the latent-sized results of the two 4096-wide dense layers): a block owns 32 float4 outputs,
+// its 8 warps each sum every 8th split with four loads in flight, warp 0 adds the 8 shares in a fixed order.
+__global__ void __launch_bounds__(256) k_reduce_partials_wide(const float* __restrict__ partial, int splits, int64_t n,
+                                                              const float* __restrict__ bias, int bias_n,
+                                                              const float* __restrict__ addend, float* __restrict__ out) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int64_t n4 = n >> 2, i = (int64_t)blockIdx.x * 32 + lane;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    const float4* src = reinterpret_cast<const float4*>(partial) + i;
+    int k = wq;
+    for (; k + 24 < splits; k += 32) {
+      const float4 v0 = __ldg(src + (size_t)k * n4), v1 = __ldg(src + (size_t)(k + 8) * n4);
+      const float4 v2 = __ldg(src + (size_t)(k + 16) * n4), v3 = __ldg(src + (size_t)(k + 24) * n4);
+      s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
+      s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; k < splits; k += 8) {
+      const float4 v = __ldg(src + (size_t)k * n4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  red[wq][lane] = s;
+  __syncthreads();
+  if (wq == 0 && i < n4) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) { const float4 v = red[g][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    if (bias) {
+      const int b = (int)((i * 4) % bias_n);
+      t.x += __ldg(bias + b); t.y += __ldg(bias + b + 1); t.z += __ldg(bias + b + 2); t.w += __ldg(bias + b + 3);
+    }
+    if (addend) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(addend) + i);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = t;
+  }
+}
+
 int reduce_partials(const float* partial, int splits, int64_t n, const float* bias, int bias_n,
                     const float* addend, float* out, cudaStream_t st) {
   AE_CHECK(n % 4 == 0 && (bias_n == 0 || bias_n % 4 == 0), "reduce_partials: sizes must be multiples of 4");
+  if (splits >= 16 && n / 4 <= 32 * 148 * 16) {
+    k_reduce_partials_wide<<<(int)((n / 4 + 31) / 32), 256, 0, st>>>(partial, splits, n, bias, bias_n, addend, out);
+    AE_LAUNCH_CHECK();
+    return 0;
+  }
   const int threads = 256;
   int64_t blocks = (n / 4 + threads - 1) / threads;
   if (blocks > 148 * 8) blocks = 148 * 8;

@@ -101,12 +101,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b);
 // 256-bit store: one full 32-byte sector per thread, so the L2 never has to fill a partially written sector from DRAM
 __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[32], int j8) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"l"(p), "f"(v[j8 * 8 + 0]), "f"(v[j8 * 8 + 1]), "f"(v[j8 * 8 + 2]), "f"(v[j8 * 8 + 3]), "f"(v[j8 * 8 + 4]),
                  "f"(v[j8 * 8 + 5]), "f"(v[j8 * 8 + 6]), "f"(v[j8 * 8 + 7])
                : "memory");
+}
+
+// 32 floats -> 32 bf16 (hi) [+ 32 bf16 (lo)] stored as full 32-byte sectors at element offset of `dst`
+template <int NSPLIT>
+__device__ __forceinline__ void st_global_split32(__nv_bfloat16* dst, size_t plane_elems, const float (&v)[32]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float a = v[2 * j], b = v[2 * j + 1];
+    hi[j] = pack_bf16x2(a, b);
+    if (NSPLIT == 2) lo[j] = pack_bf16x2(a - __bfloat162float(__float2bfloat16_rn(a)), b - __bfloat162float(__float2bfloat16_rn(b)));
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(dst + h * 16), "r"(hi[h * 8 + 0]), "r"(hi[h * 8 + 1]), "r"(hi[h * 8 + 2]), "r"(hi[h * 8 + 3]),
+                   "r"(hi[h * 8 + 4]), "r"(hi[h * 8 + 5]), "r"(hi[h * 8 + 6]), "r"(hi[h * 8 + 7])
+                 : "memory");
+    if (NSPLIT == 2)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   ::"l"(dst + plane_elems + h * 16), "r"(lo[h * 8 + 0]), "r"(lo[h * 8 + 1]), "r"(lo[h * 8 + 2]), "r"(lo[h * 8 + 3]),
+                     "r"(lo[h * 8 + 4]), "r"(lo[h * 8 + 5]), "r"(lo[h * 8 + 6]), "r"(lo[h * 8 + 7])
+                   : "memory");
+  }
 }
 
 // ---- descriptors --------------------------------------------------------------------------------

@@ -6,7 +6,9 @@
 // All kernels are persistent and work on tiles of 4 wide rows x 32 wide columns (128 wide pixels = 8 thin rows) of
 // one image.  The raw thin rows and the raw wide tile of the NEXT tile are fetched by TMA bulk copies
 // (cp.async.bulk + mbarrier, double buffered) while the current tile is computed; one in-place pass applies the
-// operand transform once per element; 128 threads, one wide pixel per thread.
+// operand transform once per element.  128 threads; in the gather every thread owns 8 consecutive wide pixels x 4
+// output channels (one 16-byte weight load and 5/3 patch loads feed 32 FMAs: the kernel is bound by FMA issue, not by
+// the shared-memory pipe).
 #include "thin_common.cuh"
 
 namespace ae {
@@ -18,7 +20,7 @@ namespace ae {
 // Both read the same staged thin rows, so the fused convT4 backward touches x / x_hat once.
 // ---------------------------------------------------------------------------------------------
 template <bool GATHER, bool WGRAD>
-__global__ void __launch_bounds__(TT_THREADS) k_thin(Operand thin, Operand wide, const float* __restrict__ w, Epilogue e,
+__global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wide, const float* __restrict__ w, Epilogue e,
                                                      float* __restrict__ out, float* __restrict__ partial, int batch) {
   extern __shared__ __align__(128) float smem_f[];
   const ThinStage L = thin_stage_layout(thin.mode, wide.mode, WGRAD);
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin(Operand thin, Operand wide,
     if (e.mode == AE_EPI_RELUBWD_STATS) {
       const int rows[4] = {AE_BNC_SCALE, AE_BNC_SHIFT, AE_BNC_MEAN, AE_BNC_RSTD};
       sbn[tid] = __ldg(e.bnc + rows[tid >> 5] * WC + lane);
+    } else if (e.mode == AE_EPI_BNRELU_SPLIT) {
+      if (tid < 64) sbn[tid] = __ldg(e.bnc + (tid >> 5 ? AE_BNC_SHIFT : AE_BNC_SCALE) * WC + lane);
     }
     if (tid < 32) { sStat[0][tid] = 0.f; sStat[1][tid] = 0.f; }
   }
@@ -57,7 +61,12 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin(Operand thin, Operand wide,
     const int st = i / (3 * XS_ROWS), r = i - st * 3 * XS_ROWS;
     stage0[st * L.floats + r * XS_PITCH + 3] = 0.f;
   }
-  float st1 = 0.f, st2 = 0.f;                             // GATHER: lane-owned channel statistics
+  // GATHER: this thread's 8 wide pixels (tile row g_r, columns g_x0 .. g_x0+7) and 4 channels (g_c0 .. g_c0+3)
+  const int g_c0 = (tid & 7) * 4, g_r = tid >> 5, g_x0 = ((tid >> 3) & 3) * 8;
+  float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};   // statistics of the thread's channels
+  float4 gbias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (GATHER && e.mode != AE_EPI_RELUBWD_STATS && e.bias) gbias = __ldg(reinterpret_cast<const float4*>(e.bias + g_c0));
+  const size_t plane_elems = (size_t)batch * WH * WW * WC;
   float bsum[3] = {0.f, 0.f, 0.f};                        // WGRAD: thin-operand sums
   // WGRAD register tile: channels c4*4..+3 x patch taps kg*7..+6 (tap 27 is padding)
   const int c4 = lane & 7, kg = lane >> 3;
@@ -111,11 +120,11 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin(Operand thin, Operand wide,
       fence_proxy_async();                                // the other stage was last touched by generic-proxy accesses
       issue(tile + gridDim.x, st ^ 1);
     }
-    float4 y4[8];                                         // RELUBWD: raw output row of this thread's pixel (prefetched)
-    const size_t row = (m0 + (size_t)warp * WW + lane) * WC;
-    if (GATHER && e.mode == AE_EPI_RELUBWD_STATS) {
+    float4 y4[8];                                         // RELUBWD: raw outputs of this thread's pixels / channels (prefetched)
+    const size_t row = (m0 + (size_t)g_r * WW + g_x0) * WC + g_c0;
+    if (GATHER && !WGRAD && e.mode == AE_EPI_RELUBWD_STATS) {   // (the fused kernel has no registers to spare: it loads in the epilogue)
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) y4[q4] = __ldg(reinterpret_cast<const float4*>(e.y + row) + q4);
+      for (int px = 0; px < 8; ++px) y4[px] = __ldg(reinterpret_cast<const float4*>(e.y + row + px * WC));
     }
     mbar_wait(bar0 + 8u * st, (it >> 1) & 1);
     // ---- transform pass (in place, once per element) ----
@@ -158,57 +167,87 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin(Operand thin, Operand wide,
     __syncthreads();
 
     if (GATHER) {
-      const int x = lane, r = warp;                     // wide pixel (r, x) of the tile
-      float acc[32];
+      float acc[8][4];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+      for (int px = 0; px < 8; ++px)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[px][j] = 0.f;
 #pragma unroll
       for (int c3 = 0; c3 < 3; ++c3) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const float* ra = xs + (c3 * XS_ROWS + 2 * r + ky) * XS_PITCH + 3 + 2 * x;
+          // thin columns 2*g_x0-1 .. 2*g_x0+15 of thin row 2*g_r-1+ky sit at p[3 .. 19] (column c is stored at index c + 4)
+          const float4* ra = reinterpret_cast<const float4*>(xs + (c3 * XS_ROWS + 2 * g_r + ky) * XS_PITCH + 2 * g_x0);
+          float p[20];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const float4 t = ra[q];
+            p[4 * q + 0] = t.x; p[4 * q + 1] = t.y; p[4 * q + 2] = t.z; p[4 * q + 3] = t.w;
+          }
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const float xa = ra[kx];
-            const float* wk = Wsm + (c3 * 9 + ky * 3 + kx) * 32;
+            const float4 wv = *reinterpret_cast<const float4*>(Wsm + (c3 * 9 + ky * 3 + kx) * 32 + g_c0);
 #pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-              const float4 wv = *reinterpret_cast<const float4*>(wk + q4 * 4);
-              acc[q4 * 4 + 0] = fmaf(xa, wv.x, acc[q4 * 4 + 0]);
-              acc[q4 * 4 + 1] = fmaf(xa, wv.y, acc[q4 * 4 + 1]);
-              acc[q4 * 4 + 2] = fmaf(xa, wv.z, acc[q4 * 4 + 2]);
-              acc[q4 * 4 + 3] = fmaf(xa, wv.w, acc[q4 * 4 + 3]);
+            for (int px = 0; px < 8; ++px) {
+              const float xa = p[2 * px + 3 + kx];
+              acc[px][0] = fmaf(xa, wv.x, acc[px][0]);
+              acc[px][1] = fmaf(xa, wv.y, acc[px][1]);
+              acc[px][2] = fmaf(xa, wv.z, acc[px][2]);
+              acc[px][3] = fmaf(xa, wv.w, acc[px][3]);
             }
           }
         }
       }
-      float s2v[32];
       if (e.mode == AE_EPI_RELUBWD_STATS) {
+        const float4 ksc = *reinterpret_cast<const float4*>(sbn + g_c0), ksh = *reinterpret_cast<const float4*>(sbn + 32 + g_c0);
+        const float4 kmu = *reinterpret_cast<const float4*>(sbn + 64 + g_c0), krs = *reinterpret_cast<const float4*>(sbn + 96 + g_c0);
+        const float sc[4] = {ksc.x, ksc.y, ksc.z, ksc.w}, sh[4] = {ksh.x, ksh.y, ksh.z, ksh.w};
+        const float mu[4] = {kmu.x, kmu.y, kmu.z, kmu.w}, rs[4] = {krs.x, krs.y, krs.z, krs.w};
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const float yv[4] = {y4[q4].x, y4[q4].y, y4[q4].z, y4[q4].w};
+        for (int px = 0; px < 8; ++px) {
+          const float4 yq = WGRAD ? __ldg(reinterpret_cast<const float4*>(e.y + row + px * WC)) : y4[px];
+          const float yv[4] = {yq.x, yq.y, yq.z, yq.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int c = q4 * 4 + j;
-            const float z = fmaf(yv[j], sbn[c], sbn[32 + c]);
-            const float d = z > 0.f ? acc[c] : 0.f;
-            acc[c] = d;
-            s2v[c] = d * ((yv[j] - sbn[64 + c]) * sbn[96 + c]);
+            const float z = fmaf(yv[j], sc[j], sh[j]);
+            const float d = z > 0.f ? acc[px][j] : 0.f;
+            acc[px][j] = d;
+            st1[j] += d;
+            st2[j] = fmaf(d, (yv[j] - mu[j]) * rs[j], st2[j]);
           }
+          *reinterpret_cast<float4*>(out + row + px * WC) = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+        }
+      } else if (e.mode == AE_EPI_BNRELU_SPLIT) {
+        // eval mode: the next layer's tensor-core operand (split-bf16 planes of BatchNorm + ReLU) straight from the accumulators
+        const float4 ksc = *reinterpret_cast<const float4*>(sbn + g_c0), ksh = *reinterpret_cast<const float4*>(sbn + 32 + g_c0);
+        const float sc[4] = {ksc.x, ksc.y, ksc.z, ksc.w}, sh[4] = {ksh.x, ksh.y, ksh.z, ksh.w};
+        const float bs[4] = {gbias.x, gbias.y, gbias.z, gbias.w};
+        __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(out);
+#pragma unroll
+        for (int px = 0; px < 8; ++px) {
+          float v[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = fmaxf(fmaf(acc[px][j] + bs[j], sc[j], sh[j]), 0.f);
+            lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+          }
+          *reinterpret_cast<uint2*>(pl + row + px * WC) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+          if (e.nsplit == 2)
+            *reinterpret_cast<uint2*>(pl + plane_elems + row + px * WC) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
         }
       } else {
+        const float bs[4] = {gbias.x, gbias.y, gbias.z, gbias.w};
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float d = acc[c] + (e.bias ? __ldg(e.bias + c) : 0.f);
-          acc[c] = d;
-          s2v[c] = d * d;
+        for (int px = 0; px < 8; ++px) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float d = acc[px][j] + bs[j];
+            acc[px][j] = d;
+            st1[j] += d;
+            st2[j] = fmaf(d, d, st2[j]);
+          }
+          *reinterpret_cast<float4*>(out + row + px * WC) = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
         }
-      }
-#pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) st_global_v8(out + row + j8 * 8, acc, j8);   // full 32-byte sectors
-      if (e.mode != AE_EPI_STORE && e.stats) {
-        st1 += warp_colsum32(acc, lane);
-        st2 += warp_colsum32(s2v, lane);
       }
     }
 
@@ -233,9 +272,17 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin(Operand thin, Operand wide,
     __syncthreads();                                      // every warp is done with stage st before it is refilled
   }
 
-  if (GATHER && e.mode != AE_EPI_STORE && e.stats) {
-    atomicAdd(&sStat[0][lane], st1);
-    atomicAdd(&sStat[1][lane], st2);
+  if (GATHER && e.mode != AE_EPI_STORE && e.mode != AE_EPI_BNRELU_SPLIT && e.stats) {
+    // lanes that share the channel group (lane bits 3, 4 = pixel group) are summed first; lanes 0..7 then hold the warp's sums
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      st1[j] += __shfl_xor_sync(0xffffffffu, st1[j], 8);  st2[j] += __shfl_xor_sync(0xffffffffu, st2[j], 8);
+      st1[j] += __shfl_xor_sync(0xffffffffu, st1[j], 16); st2[j] += __shfl_xor_sync(0xffffffffu, st2[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&sStat[0][g_c0 + j], st1[j]); atomicAdd(&sStat[1][g_c0 + j], st2[j]); }
+    }
     __syncthreads();
     if (tid < 32) {
       atomicAdd(e.stats + tid, (double)sStat[0][tid]);
@@ -295,15 +342,29 @@ __global__ void __launch_bounds__(1024) k_thin_wgrad_reduce(const float* __restr
   }
 }
 
-static int thin_blocks(int batch) {
+static int thin_blocks(int batch) {           // upper bound of every thin-kernel grid (sizes the partial buffer)
   const int tiles = batch * TILES_PER_IMAGE;
   return tiles < 4 * 148 ? tiles : 4 * 148;
 }
 size_t thin_wgrad_workspace_bytes(int batch) { return (size_t)thin_blocks(batch) * TW_PART * sizeof(float); }
 
+// Persistent grid = what is co-resident (registers allow 4 CTAs per SM; the two-source / weight-gradient stagings are
+// shared-memory limited to 2-3): a grid larger than that would run its excess CTAs as a second, nearly empty wave.
+template <typename Kernel>
+static int resident_blocks(Kernel kernel, size_t smem, int batch, int* blocks) {
+  int dev = 0, sms = 0, occ = 0;
+  AE_CUDA(cudaGetDevice(&dev));
+  AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TT_THREADS, smem));
+  AE_CHECK(occ >= 1, "thin kernel does not fit on an SM with %zu bytes of shared memory", smem);
+  const int cap = thin_blocks(batch), res = occ * sms;
+  *blocks = res < cap ? res : cap;
+  return 0;
+}
+
 template <bool GATHER, bool WGRAD>
 static int launch_thin(const Operand& thin, const Operand& wide, const float* w, const Epilogue& e, float* out,
-                       float* partial, int batch, cudaStream_t st) {
+                       float* partial, int batch, cudaStream_t st, int* blocks_out = nullptr) {
   const ThinStage L = thin_stage_layout(thin.mode, wide.mode, WGRAD);
   const size_t smem = sizeof(float) * (2 * (size_t)L.floats + 27 * 32 + 8 * 32);
   static bool attr_done = false;
@@ -314,7 +375,10 @@ static int launch_thin(const Operand& thin, const Operand& wide, const float* w,
                                  (int)(sizeof(float) * (2 * (size_t)Lmax.floats + 27 * 32 + 8 * 32))));
     attr_done = true;
   }
-  k_thin<GATHER, WGRAD><<<thin_blocks(batch), TT_THREADS, smem, st>>>(thin, wide, w, e, out, partial, batch);
+  int blocks = 0;
+  AE_TRY(resident_blocks(k_thin<GATHER, WGRAD>, smem, batch, &blocks));
+  if (blocks_out) *blocks_out = blocks;
+  k_thin<GATHER, WGRAD><<<blocks, TT_THREADS, smem, st>>>(thin, wide, w, e, out, partial, batch);
   AE_LAUNCH_CHECK();
   return 0;
 }
@@ -342,9 +406,9 @@ int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias
                int batch, cudaStream_t st) {
   AE_TRY(check_thin_operand(thin));
   AE_TRY(check_wide_operand(wide));
-  const int blocks = thin_blocks(batch);
-  AE_CHECK(bytes >= (size_t)blocks * TW_PART * sizeof(float), "thin_wgrad: workspace too small");
-  AE_TRY((launch_thin<false, true>(thin, wide, nullptr, store_epilogue(), nullptr, static_cast<float*>(partials), batch, st)));
+  int blocks = 0;
+  AE_CHECK(bytes >= (size_t)thin_blocks(batch) * TW_PART * sizeof(float), "thin_wgrad: workspace too small");
+  AE_TRY((launch_thin<false, true>(thin, wide, nullptr, store_epilogue(), nullptr, static_cast<float*>(partials), batch, st, &blocks)));
   k_thin_wgrad_reduce<<<(867 + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(partials), blocks, dw, dbias);
   AE_LAUNCH_CHECK();
   return 0;
@@ -356,82 +420,103 @@ int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, con
                    float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st) {
   AE_TRY(check_thin_operand(thin));
   AE_TRY(check_wide_operand(wide));
-  const int blocks = thin_blocks(batch);
-  AE_CHECK(bytes >= (size_t)blocks * TW_PART * sizeof(float), "thin_bwd_fused: workspace too small");
-  AE_TRY((launch_thin<true, true>(thin, wide, w, epi, out_wide, static_cast<float*>(partials), batch, st)));
+  int blocks = 0;
+  AE_CHECK(bytes >= (size_t)thin_blocks(batch) * TW_PART * sizeof(float), "thin_bwd_fused: workspace too small");
+  AE_TRY((launch_thin<true, true>(thin, wide, w, epi, out_wide, static_cast<float*>(partials), batch, st, &blocks)));
   k_thin_wgrad_reduce<<<(867 + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(partials), blocks, dw, dbias);
   AE_LAUNCH_CHECK();
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// wide -> thin scatter + sigmoid (+ squared error): convT4 forward.  The transformed wide tile (9 rows x 33
-// columns with a zero halo) is staged once; every thread produces the 2x2x3 output quads of two vertically
-// adjacent wide pixels (no atomics on the output).
+// wide -> thin scatter + sigmoid (+ squared error): convT4 forward.  The transformed wide tile (5 rows x 33
+// columns with a zero halo) is staged once; four lanes share a strip of 4 wide pixels, each summing a quarter of the
+// input channels for all 4 output quads, then a register reduce-scatter hands every lane one pixel's 2x2x3 quad
+// (no atomics on the output).
 // ---------------------------------------------------------------------------------------------
 static constexpr int AS_ROWS = TILE_ROWS + 1, AS_COLS = WW + 1;
 
-__global__ void __launch_bounds__(TT_THREADS) k_thin_scatter_sigmoid(Operand wide, const float* __restrict__ w,
+__global__ void __launch_bounds__(TT_THREADS, 4) k_thin_scatter_sigmoid(Operand wide, const float* __restrict__ w,
                                                                      const float* __restrict__ bias, float* __restrict__ x_hat,
                                                                      const float* __restrict__ x, double* __restrict__ sse,
                                                                      int batch) {
-  extern __shared__ __align__(16) float smem_f[];
-  float* as = smem_f;                                   // [AS_ROWS][AS_COLS][32], 16-byte chunk c of pixel p at c ^ (p & 7)
+  extern __shared__ __align__(128) float smem_f[];
+  float* raw = smem_f;                                  // [AS_ROWS][32][32]: the tile's wide rows + the halo row, one bulk copy
+  float* as = raw + AS_ROWS * WW * WC;                  // [AS_ROWS][AS_COLS][32] transformed, 16-byte chunk c of pixel p at c ^ (p & 7)
   float* Wsm = as + AS_ROWS * AS_COLS * 32;             // [9 taps][3 co][32 ci]
+  float* sbn = Wsm + 27 * 32;                           // [2][32] scale, shift of the wide operand
+  __shared__ __align__(8) uint64_t bar_raw;
   __shared__ float red[TT_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 27 * 32; i += TT_THREADS) {
-    const int ci = i / 27, r = i - ci * 27, co = r / 9, tap = r - co * 9;
-    Wsm[(tap * 3 + co) * 32 + ci] = __ldg(w + i);
+  const uint32_t bar = smem_u32(&bar_raw);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
   }
+  for (int o = tid; o < 27 * 32; o += TT_THREADS) {     // o = (tap*3 + co)*32 + ci  <-  w[ci][co][tap]
+    const int ci = o & 31, r = o >> 5, tap = r / 3, co = r - tap * 3;
+    Wsm[o] = __ldg(w + ci * 27 + co * 9 + tap);
+  }
+  if (tid < 64)
+    sbn[tid] = wide.mode == AE_OP_BNRELU ? __ldg(wide.bnc + (tid >> 5 ? AE_BNC_SHIFT : AE_BNC_SCALE) * WC + lane) : (tid >> 5 ? 0.f : 1.f);
   const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
   float err = 0.f;
   const int tiles = batch * TILES_PER_IMAGE;
   constexpr int UNITS = AS_ROWS * AS_COLS * 8;
-  constexpr int ITER = (UNITS + TT_THREADS - 1) / TT_THREADS;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  // one thread: fetch the raw rows of `tile` (the image's last tile has no halo row below it)
+  auto issue = [&](int tile) {
     const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;
-    __syncthreads();
-    {
-      float4 buf[ITER];
-#pragma unroll
-      for (int j = 0; j < ITER; ++j) {
-        const int i = tid + j * TT_THREADS;
-        const int q = i & 7, p = i >> 3;
-        const int pr = p / AS_COLS, pc = p - pr * AS_COLS;
-        const int iy = tr * TILE_ROWS + pr;
-        const bool valid = i < UNITS && iy < WH && pc < WW;
-        const size_t off = (((size_t)n * WH + iy) * WW + pc) * WC + q * 4;
-        buf[j] = load_operand4(wide, valid ? off : 0, q * 4, valid);
+    const uint32_t bytes = (uint32_t)((tr == TILES_PER_IMAGE - 1 ? TILE_ROWS : AS_ROWS) * WW * WC * 4);
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_copy_g2s(smem_u32(raw), wide.src + ((size_t)n * WH + tr * TILE_ROWS) * WW * WC, bytes, bar);
+  };
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < tiles) issue(blockIdx.x);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;
+    mbar_wait(bar, it & 1);
+    // transform pass: raw -> BatchNorm + ReLU -> swizzled tile with a zero halo (right column, row below the image)
+    for (int i = tid; i < UNITS; i += TT_THREADS) {
+      const int q = i & 7, p = i >> 3;
+      const int pr = p / AS_COLS, pc = p - pr * AS_COLS;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tr * TILE_ROWS + pr < WH && pc < WW) {
+        v = *reinterpret_cast<const float4*>(raw + (pr * WW + pc) * WC + q * 4);
+        if (wide.mode == AE_OP_BNRELU) {
+          const float4 sc = *reinterpret_cast<const float4*>(sbn + q * 4), sh = *reinterpret_cast<const float4*>(sbn + 32 + q * 4);
+          v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+          v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+        }
       }
-#pragma unroll
-      for (int j = 0; j < ITER; ++j) {
-        const int i = tid + j * TT_THREADS;
-        if (i >= UNITS) break;
-        const int q = i & 7, p = i >> 3;
-        *reinterpret_cast<float4*>(as + p * 32 + ((q ^ (p & 7)) << 2)) = buf[j];
-      }
+      *reinterpret_cast<float4*>(as + p * 32 + ((q ^ (p & 7)) << 2)) = v;
     }
-    __syncthreads();
-    // wide pixel (warp, lane): acc[py][px][co] of its 2x2 output quad
-    float acc[2][2][3];
+    __syncthreads();                                    // `as` complete, `raw` consumed
+    if (tid == 0 && tile + (int)gridDim.x < tiles) {    // the next tile's rows arrive while this one is computed
+      fence_proxy_async();
+      issue(tile + gridDim.x);
+    }
+    // Thread (warp = tile row, strip = lane >> 2, ciq = lane & 3): the 2x2x3 output quads of the strip's 4 wide pixels,
+    // summed over input channels {ciq*4 .. +3} and {16 + ciq*4 .. +3}; one weight load feeds 16 FMAs.  A two-stage
+    // reduce-scatter over the 4 ciq lanes then leaves lane ciq with the complete sums of pixel ciq of the strip.
+    const int x0 = (lane >> 2) * 4, ciq = lane & 3;
+    float acc[4][12];                                   // [pixel of the strip][(py*2 + px)*3 + co]
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[a][b][c] = 0.f;
+      for (int b = 0; b < 12; ++b) acc[a][b] = 0.f;
     // source pixel (iy+dy, ix+dx) contributes to output parity (py,px) through tap (ky,kx):
     //   dy=0: py=0 -> ky=1 ; py=1 -> ky=2        dy=1: py=1 -> ky=0      (same for x)
-#pragma unroll 1
-    for (int q4 = 0; q4 < 8; ++q4) {
-      float4 v[2][2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int q4 = ciq + 4 * half;
+      float4 v[2][5];
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int p = (warp + dy) * AS_COLS + lane + dx;
-          v[dy][dx] = *reinterpret_cast<const float4*>(as + p * 32 + ((q4 ^ (p & 7)) << 2));
+        for (int c = 0; c < 5; ++c) {
+          const int p = (warp + dy) * AS_COLS + x0 + c;
+          v[dy][c] = *reinterpret_cast<const float4*>(as + p * 32 + ((q4 ^ (p & 7)) << 2));
         }
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
@@ -446,21 +531,44 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin_scatter_sigmoid(Operand wid
 #pragma unroll
               for (int co = 0; co < 3; ++co) {
                 const float4 wv = *reinterpret_cast<const float4*>(Wsm + ((ky * 3 + kx) * 3 + co) * 32 + q4 * 4);
-                const float4 vv = v[dy][dx];
-                acc[py][px][co] = fmaf(vv.x, wv.x, fmaf(vv.y, wv.y, fmaf(vv.z, wv.z, fmaf(vv.w, wv.w, acc[py][px][co]))));
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                  const float4 vv = v[dy][a + dx];
+                  float& t = acc[a][(py * 2 + px) * 3 + co];
+                  t = fmaf(vv.x, wv.x, fmaf(vv.y, wv.y, fmaf(vv.z, wv.z, fmaf(vv.w, wv.w, t))));
+                }
               }
             }
           }
     }
-    const int ty0 = 2 * (tr * TILE_ROWS + warp);        // first of this thread's two thin rows
+    float r1[2][12], r2[12];
+    {
+      const bool hi = (ciq & 2) != 0;                   // stage 1 (partner lane ^ 2): keep pixels {0,1} or {2,3}
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 12; ++b) {
+          const float send = hi ? acc[a][b] : acc[a + 2][b];
+          const float keep = hi ? acc[a + 2][b] : acc[a][b];
+          r1[a][b] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+      const bool odd = (ciq & 1) != 0;                  // stage 2 (partner lane ^ 1): keep the first or the second of the pair
+#pragma unroll
+      for (int b = 0; b < 12; ++b) {
+        const float send = odd ? r1[0][b] : r1[1][b];
+        const float keep = odd ? r1[1][b] : r1[0][b];
+        r2[b] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+    }
+    const int ty0 = 2 * (tr * TILE_ROWS + warp);        // first of this thread's two thin rows; its wide column is x0 + ciq
 #pragma unroll
     for (int co = 0; co < 3; ++co) {
       const float b = co == 0 ? b0 : (co == 1 ? b1 : b2);
 #pragma unroll
       for (int py = 0; py < 2; ++py) {
-        const size_t o = (((size_t)n * 3 + co) * TH + ty0 + py) * TW + 2 * lane;
-        const float s0 = 1.f / (1.f + expf(-(acc[py][0][co] + b)));
-        const float s1 = 1.f / (1.f + expf(-(acc[py][1][co] + b)));
+        const size_t o = (((size_t)n * 3 + co) * TH + ty0 + py) * TW + 2 * (x0 + ciq);
+        const float s0 = 1.f / (1.f + expf(-(r2[(py * 2 + 0) * 3 + co] + b)));
+        const float s1 = 1.f / (1.f + expf(-(r2[(py * 2 + 1) * 3 + co] + b)));
         *reinterpret_cast<float2*>(x_hat + o) = make_float2(s0, s1);
         if (x) {
           const float2 t = __ldg(reinterpret_cast<const float2*>(x + o));
@@ -468,6 +576,7 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin_scatter_sigmoid(Operand wid
         }
       }
     }
+    __syncthreads();                                    // every warp is done with `as` before the next tile's transform
   }
   if (x && sse) {
     err = warp_sum(err);
@@ -479,13 +588,17 @@ __global__ void __launch_bounds__(TT_THREADS) k_thin_scatter_sigmoid(Operand wid
 
 int thin_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* bias, float* x_hat, const float* x,
                              double* sse, int batch, cudaStream_t st) {
-  const size_t smem = sizeof(float) * (AS_ROWS * AS_COLS * 32 + 27 * 32);
+  AE_CHECK(wide.mode == AE_OP_RAW || wide.mode == AE_OP_BNRELU, "thin_scatter: wide operand mode %d not supported", wide.mode);
+  AE_CHECK(((uintptr_t)wide.src & 15) == 0, "thin_scatter: the wide tensor must be 16-byte aligned");
+  const size_t smem = sizeof(float) * (AS_ROWS * WW * WC + AS_ROWS * AS_COLS * 32 + 27 * 32 + 64);
   static bool attr_done = false;
   if (!attr_done) {
     AE_CUDA(cudaFuncSetAttribute(k_thin_scatter_sigmoid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_thin_scatter_sigmoid<<<thin_blocks(batch), TT_THREADS, smem, st>>>(wide, w, bias, x_hat, x, sse, batch);
+  int blocks = 0;
+  AE_TRY(resident_blocks(k_thin_scatter_sigmoid, smem, batch, &blocks));
+  k_thin_scatter_sigmoid<<<blocks, TT_THREADS, smem, st>>>(wide, w, bias, x_hat, x, sse, batch);
   AE_LAUNCH_CHECK();
   return 0;
 }

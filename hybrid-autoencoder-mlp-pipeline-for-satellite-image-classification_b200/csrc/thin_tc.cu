@@ -396,6 +396,7 @@ static int check_ops(const Operand& thin, const Operand* wide) {
 
 int thin_tc_gather_fwd(const Operand& thin, const float* w, const Epilogue& epi, float* out, int batch, int nsplit, cudaStream_t st) {
   AE_TRY(check_ops(thin, nullptr));
+  AE_CHECK(epi.mode != AE_EPI_BNRELU_SPLIT, "thin_tc_gather_fwd: the split-bf16 epilogue is implemented by the CUDA-core kernel only");
   const Operand none = raw_operand(nullptr);
   return nsplit == 2 ? launch_thin_tc<true, false, 2>(thin, none, w, epi, out, nullptr, batch, st)
                      : launch_thin_tc<true, false, 1>(thin, none, w, epi, out, nullptr, batch, st);

@@ -204,8 +204,8 @@ struct alignas(64) TmaRow {
   int bx, by, bn;           // pixel box of one 128-row tile
 };
 
-// Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A tile is (phase, n-tile, m-tile) with
-// the m-tile fastest.  The accumulator is double-buffered in tensor memory, so the epilogue of tile i overlaps the
+// Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A tile is (phase, m-tile, n-tile) with
+// the n-tile fastest.  The accumulator is double-buffered in tensor memory, so the epilogue of tile i overlaps the
 // TMA loads and MMAs of tile i+1, and barrier / TMEM set-up is paid once per CTA.
 template <int FAMILY, int NT, int KC, int NSPLIT, int STAGES>
 __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constant__ TmaRow q) {
@@ -247,6 +247,10 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
       const int ch = c % q.epi.C;
       k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
                       __ldg(q.epi.bnc + AE_BNC_MEAN * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_RSTD * q.epi.C + ch));
+    } else if (q.epi.mode == AE_EPI_BNRELU_SPLIT) {           // relu(scale*(acc + bias) + shift), rounded exactly as the two-pass form
+      const int ch = c % q.epi.C;
+      k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
+                      q.epi.bias ? __ldg(q.epi.bias + c) : 0.f, 0.f);
     } else if (q.epi.bias) {
       k.x = __ldg(q.epi.bias + c);
     }
@@ -260,10 +264,13 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
 
   // tile -> (phase, ntile, m0, number of K chunks, first chunk inside the weight pack)
   auto decode = [&](int tile, int& phase, int& ntile, int& m0, int& nkc, int& kc_off) {
+    // n-tile fastest: the CTAs working on one m-tile at the same time share its A boxes through the L2 (with the m-tile
+    // fastest, an operand larger than the L2 was re-read from DRAM once per n-tile)
     phase = tile / tiles_mn;
     const int rem = tile - phase * tiles_mn;
-    ntile = rem / tiles_m;
-    m0 = (rem - ntile * tiles_m) * TILE_M;
+    const int mt = rem / tiles_n;
+    ntile = rem - mt * tiles_n;
+    m0 = mt * TILE_M;
     if (FAMILY == FAM_DGRAD) {
       const int py = phase >> 1, px = phase & 1;
       nkc = (1 + py) * (1 + px) * q.cpt;
@@ -392,6 +399,12 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
               s2[j4 * 4 + j] = d * ((ya[j] - k.z) * k.w);
             }
           }
+        } else if (e.mode == AE_EPI_BNRELU_SPLIT) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 k = *reinterpret_cast<const float4*>(&sCoef[n + j][0]);
+            v[j] = fmaxf(fmaf(v[j] + k.z, k.x, k.y), 0.f);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -402,8 +415,13 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
           }
         }
         if (row_ok) {
+          if (e.mode == AE_EPI_BNRELU_SPLIT) {
+            const size_t plane = (size_t)q.M * q.N * (FAMILY == FAM_DGRAD ? 4 : 1);
+            st_global_split32<NSPLIT>(reinterpret_cast<__nv_bfloat16*>(q.out) + orow + n, plane, v);
+          } else {
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) st_global_v8(q.out + orow + n + j8 * 8, v, j8);
+            for (int j8 = 0; j8 < 4; ++j8) st_global_v8(q.out + orow + n + j8 * 8, v, j8);
+          }
         }
         if (do_stats) {
           const float a = warp_colsum32_tc(v, lane);

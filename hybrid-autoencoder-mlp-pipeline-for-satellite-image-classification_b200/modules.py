@@ -37,6 +37,11 @@ def default_backend() -> str:
     return os.environ.get("AE_B200_BACKEND", "tc")
 
 
+def eval_chunk() -> int:
+    """Images per engine call of an eval-mode encoder pass over a larger batch."""
+    return max(64, int(os.environ.get("AE_B200_EVAL_CHUNK", "4096")))
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"ae_b200: {what} must be a CUDA tensor (no CPU fallback); got device {t.device}")
@@ -93,6 +98,7 @@ class _Engine:
         self.run_off = {}
         self.step_off = {}
         self.packed_version = None
+        self.instance = 0        # bumped whenever the native engine (and its workspace) is re-created
 
     def register(self, part: int, params: List[nn.Parameter], bns: List[nn.Module]):
         self.parts[part] = dict(params=params, bns=bns)
@@ -121,6 +127,7 @@ class _Engine:
         h = C.c_void_p()
         check(lib.ae_engine_create(C.byref(cfg), C.byref(h)))
         self.handle, self.max_batch, self.device = h, cap, device
+        self.instance += 1
         nbytes = lib.ae_engine_workspace_bytes(h)
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
         base = self.workspace.data_ptr()
@@ -231,8 +238,19 @@ class _EncoderFn(torch.autograd.Function):
             raise RuntimeError(f"ae_b200: expected images of shape [B,3,64,64], got {tuple(x.shape)}")
         x = x.contiguous()
         b = x.shape[0]
-        engine.prepare(x.device, b)
         z = torch.empty(b, engine.latent_dim, dtype=torch.float32, device=x.device)
+        if not training and b > eval_chunk():
+            # inference over a large batch (BASELINE config 5: 1k-64k images): images are independent in eval mode, so
+            # the batch is walked in chunks and the workspace stays bounded (2.5 MB per image of the chunk)
+            n = eval_chunk()
+            engine.prepare(x.device, n)
+            lib = _lib.load()
+            for i in range(0, b, n):
+                m = min(n, b - i)
+                check(lib.ae_encoder_forward(engine.handle, ptr(x[i:i + m]), m, 0, ptr(z[i:i + m]), stream_ptr()))
+            ctx.engine, ctx.b = engine, b
+            return z
+        engine.prepare(x.device, b)
         check(_lib.load().ae_encoder_forward(engine.handle, ptr(x), b, int(training), ptr(z), stream_ptr()))
         ctx.engine, ctx.b = engine, b
         ctx.save_for_backward(x)

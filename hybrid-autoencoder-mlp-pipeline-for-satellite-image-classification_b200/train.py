@@ -43,6 +43,7 @@ class TrainStep:
         self.handle = h
         self.stream.synchronize()
         self._eng = eng
+        self._instance = eng.instance
         self.num_kernels = lib.ae_step_graph_num_kernels(h)
 
     def load(self, imgs: torch.Tensor, labels: torch.Tensor):
@@ -52,6 +53,10 @@ class TrainStep:
             self.y.copy_(labels, non_blocking=True)
 
     def run(self):
+        if self._eng.instance != self._instance:
+            # the captured graph addresses the workspace of the engine it was captured on
+            raise RuntimeError("ae_b200: the model's engine was re-created (a larger batch was run through it) after this "
+                               "TrainStep was captured; build a new TrainStep")
         check(_lib.load().ae_step_graph_launch(self.handle, C.c_void_p(self.stream.cuda_stream)))
         self._eng.flat.generation += 1
         self._eng.mark_packed()      # the graph re-packs the weights itself

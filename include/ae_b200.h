@@ -71,7 +71,9 @@ typedef struct ae_operand {
 enum {
   AE_EPI_STORE = 0,          /* out = acc (+ bias) */
   AE_EPI_BIAS_STATS = 1,     /* out = acc + bias; stats[c] += sum(out), stats[C+c] += sum(out^2)  (feeds BatchNorm) */
-  AE_EPI_RELUBWD_STATS = 2   /* out = acc * (scale*y+shift > 0); stats[c] += sum(out), stats[C+c] += sum(out * xhat) */
+  AE_EPI_RELUBWD_STATS = 2,  /* out = acc * (scale*y+shift > 0); stats[c] += sum(out), stats[C+c] += sum(out * xhat) */
+  AE_EPI_BNRELU_SPLIT = 3    /* eval-mode fusion: `out` receives split-bf16 planes of relu(scale*(acc+bias)+shift) (bnc = the
+                                layer's coefficient block from running statistics): the next GEMM's operand, no fp32 pass */
 };
 
 typedef struct ae_epilogue {

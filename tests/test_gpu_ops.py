@@ -149,6 +149,88 @@ def test_conv_wgrad(shape, prec, backend):
     assert gu.rel(dw.cpu(), ref) <= gu.TOL[prec]
 
 
+def _decode_planes(planes, shape, prec):
+    """split-bf16 planes [nsplit][...shape] (uint8 buffer) -> fp32 tensor hi (+ lo)"""
+    ns = 2 if prec == "fp32" else 1
+    t = planes.view(torch.bfloat16)[: ns * int(np.prod(shape))].view(ns, *shape).float()
+    return t.sum(0)
+
+
+@pytest.mark.parametrize("prec", gu.PRECISIONS)
+@pytest.mark.parametrize("family", ["fwd", "dgrad"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_fused_bnrelu_split_epilogue(shape, family, prec):
+    """Eval-mode fusion (AE_EPI_BNRELU_SPLIT): the epilogue writes split-bf16 planes of relu(bn(conv + bias)), i.e. exactly
+    what ae_split_operand(BNRELU) makes of the fp32 output of the two-pass form."""
+    if "tc" not in gu.BACKENDS:
+        pytest.skip("tcgen05 path only")
+    b, hs, cb, cs = shape
+    rs = np.random.RandomState(hash((shape, family)) % 2 ** 31)
+    d = gu.dev()
+    w = torch.from_numpy((rs.standard_normal((cs, cb, 3, 3)) / np.sqrt(9 * cb)).astype(np.float32))
+    pf, pd = gu.pack_conv(w.to(d), cs, cb, prec, "tc")
+    g = _geom(b, hs, cb, cs)
+    if family == "fwd":
+        cin, cout, hin, hout = cb, cs, 2 * hs, hs
+    else:
+        cin, cout, hin, hout = cs, cb, hs, 2 * hs
+    a = torch.from_numpy(rs.standard_normal((b, cin, hin, hin)).astype(np.float32))
+    bias = torch.from_numpy(rs.uniform(-0.1, 0.1, cout).astype(np.float32))
+    bnc = gu.make_bnc(cout, rs, "cpu")
+    ad, biasd, bncd = gu.nhwc(a).to(d), bias.to(d), bnc.to(d)
+    op, _keep = gu.conv_operand("tc", prec, cin, ad)
+    fn = gu.lib().ae_conv2d_s2_fwd if family == "fwd" else gu.lib().ae_conv2d_s2_dgrad
+    pk = pf if family == "fwd" else pd
+    # two-pass form: fp32 output, then BatchNorm + ReLU + split
+    y = torch.empty(b, hout, hout, cout, device=d)
+    ep = gu.epilogue(_lib.EPI_STORE, biasd)
+    _lib.check(fn(C.byref(g), C.byref(op), gu.p(pk), C.byref(ep), gu.p(y), gu.PREC[prec], gu.BACK["tc"], gu.stream()))
+    want = torch.empty(gu.lib().ae_split_operand_bytes(y.numel(), gu.PREC[prec]), dtype=torch.uint8, device=d)
+    op2 = gu.operand(y, None, bncd, 0.0, _lib.OP_BNRELU)
+    _lib.check(gu.lib().ae_split_operand(C.byref(op2), cout, y.numel(), gu.p(want), gu.PREC[prec], gu.stream()))
+    # fused form
+    got = torch.full_like(want, 0x7f)
+    epf = gu.epilogue(_lib.EPI_BNRELU_SPLIT, biasd, None, bncd)
+    _lib.check(fn(C.byref(g), C.byref(op), gu.p(pk), C.byref(epf), gu.p(got), gu.PREC[prec], gu.BACK["tc"], gu.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), "fused epilogue planes differ from the two-pass planes"
+    # and against the CPU reference of the layer
+    if family == "fwd":
+        ref = F.conv2d(a, w, bias, stride=2, padding=1)
+    else:
+        ref = F.conv_transpose2d(a, w, bias, stride=2, padding=1, output_padding=1)
+    ref = _apply_operand_cpu(_lib.OP_BNRELU, ref, None, bnc)
+    assert gu.rel(gu.nchw(_decode_planes(got, (b, hout, hout, cout), prec)).cpu(), ref) <= 2 * gu.TOL[prec]
+
+
+@pytest.mark.parametrize("prec", gu.PRECISIONS)
+@pytest.mark.parametrize("batch", [1, 5])
+def test_thin_gather_fused_bnrelu_split_epilogue(batch, prec):
+    """Conv2d(3,32) with the eval-mode epilogue: planes of relu(bn(conv1(x) + b)) bit-identical to the two-pass form."""
+    rs = np.random.RandomState(300 + batch)
+    d = gu.dev()
+    x = torch.from_numpy(rs.random_sample((batch, 3, 64, 64)).astype(np.float32))
+    w1 = torch.from_numpy((rs.standard_normal((32, 3, 3, 3)) / 5).astype(np.float32))
+    b1 = torch.from_numpy(rs.uniform(-0.1, 0.1, 32).astype(np.float32))
+    bnc = gu.make_bnc(32, rs, "cpu")
+    xd, w1d, b1d, bncd = x.to(d), w1.to(d), b1.to(d), bnc.to(d)
+    pb = (gu.PREC[prec], gu.BACK["simt"])
+    op = gu.operand(xd)
+    y = torch.empty(batch, 32, 32, 32, device=d)
+    ep = gu.epilogue(_lib.EPI_STORE, b1d)
+    _lib.check(gu.lib().ae_thin_gather_fwd(C.byref(op), gu.p(w1d), C.byref(ep), gu.p(y), batch, *pb, gu.stream()))
+    want = torch.empty(gu.lib().ae_split_operand_bytes(y.numel(), gu.PREC[prec]), dtype=torch.uint8, device=d)
+    op2 = gu.operand(y, None, bncd, 0.0, _lib.OP_BNRELU)
+    _lib.check(gu.lib().ae_split_operand(C.byref(op2), 32, y.numel(), gu.p(want), gu.PREC[prec], gu.stream()))
+    got = torch.full_like(want, 0x7f)
+    epf = gu.epilogue(_lib.EPI_BNRELU_SPLIT, b1d, None, bncd)
+    _lib.check(gu.lib().ae_thin_gather_fwd(C.byref(op), gu.p(w1d), C.byref(epf), gu.p(got), batch, *pb, gu.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    ref = _apply_operand_cpu(_lib.OP_BNRELU, F.conv2d(x, w1, b1, stride=2, padding=1), None, bnc)
+    assert gu.rel(gu.nchw(_decode_planes(got, (batch, 32, 32, 32), prec)).cpu(), ref) <= gu.TOL[prec]
+
+
 @pytest.mark.parametrize("backend", gu.BACKENDS)
 @pytest.mark.parametrize("batch", [1, 3, 16])
 def test_thin_layers(batch, backend):
