@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libae_b200.so")
-SOURCES = ["api.cu", "simt_gemm.cu", "thin.cu", "thin_tc.cu", "elementwise.cu", "head.cu", "mlp.cu", "tma_gemm.cu", "engine.cu", "dp.cu"]
+SOURCES = ["api.cu", "simt_gemm.cu", "thin.cu", "thin_tc.cu", "elementwise.cu", "head.cu", "mlp.cu", "tma_gemm.cu", "engine.cu", "dp.cu", "augment.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -52,12 +52,13 @@ class TrainStep:
             self.x.copy_(imgs, non_blocking=True)
             self.y.copy_(labels, non_blocking=True)
 
-    def run(self):
+    def run(self, stream=None):
+        """Replay the captured step on `stream` (default: this TrainStep's own stream)."""
         if self._eng.instance != self._instance:
             # the captured graph addresses the workspace of the engine it was captured on
             raise RuntimeError("ae_b200: the model's engine was re-created (a larger batch was run through it) after this "
                                "TrainStep was captured; build a new TrainStep")
-        check(_lib.load().ae_step_graph_launch(self.handle, C.c_void_p(self.stream.cuda_stream)))
+        check(_lib.load().ae_step_graph_launch(self.handle, C.c_void_p((stream or self.stream).cuda_stream)))
         self._eng.flat.generation += 1
         self._eng.mark_packed()      # the graph re-packs the weights itself
 
@@ -129,8 +130,44 @@ class TrainStep:
         torch.cuda.current_stream(dev).wait_stream(ms)
         return out
 
+    def _sibling(self, batch: int) -> "TrainStep":
+        """The same step captured for another batch size (the loader's last, smaller batch); shares model, optimizer
+        state and workspace."""
+        if not hasattr(self, "_siblings"):
+            self._siblings = {}
+        sib = self._siblings.get(batch)
+        if sib is None:
+            if batch > self.batch:
+                raise RuntimeError("ae_b200: a loader batch larger than the TrainStep's batch size")
+            sib = TrainStep(self.model, self.opt, self.alpha, batch, comm=self.comm, device=self.device)
+            self._siblings[batch] = sib
+        return sib
+
+    def run_loader(self, loader):
+        """One training epoch, NB:2672-2688, over an ``ae_b200.data.DeviceLoader``: every batch is gathered / augmented
+        straight into the graph's input buffer by one kernel, the step graph is replayed, and the step's loss is kept in
+        a device-side history; the host synchronises ONCE, at the end (the reference synchronises every step through
+        ``loss.item()``, NB:2687).  Returns (losses [steps,3] host tensor of [loss, mse, ce], batch sizes list)."""
+        dev, ds = self.device, loader.dataset
+        hist = torch.zeros(len(loader), 4, dtype=torch.float32, device=dev)
+        sizes = []
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            for k, idx in enumerate(loader.batches()):
+                b = int(idx.numel())
+                st = self if b == self.batch else self._sibling(b)
+                loader.transform(ds.images, idx, out=st.x)
+                torch.index_select(ds.labels, 0, idx, out=st.y)
+                st.run(self.stream)
+                hist[k].copy_(st.loss, non_blocking=True)
+                sizes.append(b)
+        self.stream.synchronize()
+        return hist[:len(sizes), :3].cpu(), sizes
+
     def close(self):
         """Destroy the captured graph (required before the NCCL communicator it references is destroyed)."""
+        for sib in getattr(self, "_siblings", {}).values():
+            sib.close()
         if getattr(self, "handle", None):
             self.stream.synchronize()
             _lib.load().ae_step_graph_destroy(self.handle)

@@ -237,6 +237,20 @@ int ae_adam_step_flat(float* p, const float* g, float* m, float* v, int64_t n, f
                       float beta2, float eps, float weight_decay, float grad_scale, int* step_dev,
                       ae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * ae_augment_u8 -- the reference's input transforms on the device:
+ *   training  NB:386-391  RandomHorizontalFlip -> RandomCrop(64, padding=pad) -> ToTensor -> AddGaussianNoise (NB:361-368)
+ *   eval      NB:393-395  ToTensor                      (flip = off_y = off_x = noise = NULL, noise_std = 0)
+ * images: [num_images,64,64,3] uint8 HWC resident on the device; index[b] (or b) selects the source of output b
+ * (the shuffled batch of the DataLoader, NB:420).  flip[b] != 0 mirrors the image first; (off_y[b], off_x[b]) in
+ * [0, 2*pad] are RandomCrop's (i, j) into the zero-padded image (pad, pad = no shift).  out: [batch,3,64,64] fp32 =
+ * value/255 + (n*noise_std + noise_mean), n from `noise` ([batch,3,64,64] fp32) if given, else -- when noise_std != 0 --
+ * standard normals drawn from Philox4x32-10 keyed by (seed, element index).
+ * ---------------------------------------------------------------------------------------- */
+int ae_augment_u8(const uint8_t* images, int64_t num_images, const int64_t* index, const uint8_t* flip,
+                  const int32_t* off_y, const int32_t* off_x, int pad, const float* noise, uint64_t seed,
+                  float noise_mean, float noise_std, float* out, int batch, ae_stream_t stream);
+
 /* layout helpers at the boundary (NCHW fp32 <-> NHWC fp32 / bf16) */
 int ae_layout_nchw_f32_to_nhwc_f32(const float* src, float* dst, int n, int c, int h, int w, ae_stream_t stream);
 int ae_layout_nhwc_f32_to_nchw_f32(const float* src, float* dst, int n, int c, int h, int w, ae_stream_t stream);

@@ -111,3 +111,19 @@ def test_encode_predict():
     gu.check(g, "z", z.numpy(), TOL)
     gu.check(g, "logits", logits.numpy(), TOL)
     assert np.array_equal(logits.argmax(1).numpy(), g["argmax"])
+
+
+def test_augment_oracle_matches_reference_transforms():
+    """oracle/augment_port.py against the outputs of the reference's own torchvision Compose objects (NB:386-395),
+    recorded by oracle/make_golden_augment.py: bit-exact, including the order of the random draws."""
+    import os
+    from oracle import augment_port as ap
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "augment_B6.npz"))
+    assert len(set(g["flip"].tolist())) == 2, "fixture must cover flipped and unflipped images"
+    for i in range(g["images"].shape[0]):
+        flip, oy, ox, noise = ap.draws_like_reference(int(g["seeds"][i]))
+        assert (flip, oy, ox) == (bool(g["flip"][i]), int(g["off_y"][i]), int(g["off_x"][i]))
+        assert np.array_equal(noise.numpy(), g["noise"][i])
+        out = ap.train_transform(g["images"][i], flip, oy, ox, noise)
+        assert np.array_equal(out.numpy(), g["train_out"][i])
+        assert np.array_equal(ap.to_tensor(g["images"][i]).numpy(), g["eval_out"][i])
