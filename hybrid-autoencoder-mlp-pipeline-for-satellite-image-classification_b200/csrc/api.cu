@@ -23,7 +23,7 @@ int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias
                int batch, cudaStream_t st);
 size_t thin_wgrad_workspace_bytes(int batch);
 int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
-                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st);
+                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st, int phase);
 int thin_tc_gather_fwd(const Operand& thin, const float* w, const Epilogue& epi, float* out, int batch, int nsplit, cudaStream_t st);
 int thin_tc_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes, int batch,
                   int nsplit, cudaStream_t st);
@@ -190,7 +190,7 @@ int ae_thin_bwd_fused(const ae_operand_t* wide, const ae_operand_t* thin, const 
     return thin_tc_bwd_fused(make_operand(wide, 32), make_operand(thin, 3), w, make_epilogue(epi, 32), out_wide, dw, dbias_thin,
                              partials, partials_bytes, batch, nsplit_of(precision), (cudaStream_t)stream);
   return thin_bwd_fused(make_operand(wide, 32), make_operand(thin, 3), w, make_epilogue(epi, 32), out_wide, dw, dbias_thin,
-                        partials, partials_bytes, batch, (cudaStream_t)stream);
+                        partials, partials_bytes, batch, (cudaStream_t)stream, 0);
 }
 
 int ae_bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float* running_mean,

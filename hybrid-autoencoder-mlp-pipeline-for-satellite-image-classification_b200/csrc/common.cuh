@@ -83,6 +83,8 @@ struct BnJob {
   float* dbeta;
   int C;
   int training;
+  int64_t* nbt;      // FINALIZE, training: this layer's num_batches_tracked, incremented by the job (or NULL)
+  float* dzero;      // BWD: C floats set to zero by the job -- the gradient of the bias that feeds this BatchNorm (or NULL)
 };
 
 struct Geom {

@@ -12,9 +12,10 @@ static constexpr double BN_MOMENTUM = 0.1;
 // ---------------------------------------------------------------------------------------------
 __global__ void k_bn_finalize(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
-                              float* __restrict__ bnc, int C, int training) {
+                              float* __restrict__ bnc, int C, int training, int64_t* __restrict__ nbt) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (c == 0 && training && nbt) *nbt += 1;
   double mean, var;
   if (training) {
     mean = stats[c] / count;
@@ -41,7 +42,7 @@ int bn_finalize(const double* stats, int64_t count, const float* gamma, const fl
                 float* rvar, float* bnc, int C, int training, cudaStream_t st) {
   AE_CHECK(training || (rmean && rvar), "bn_finalize: eval mode needs running statistics");
   AE_CHECK(!training || stats, "bn_finalize: training mode needs batch statistics");
-  k_bn_finalize<<<(C + 127) / 128, 128, 0, st>>>(stats, (double)count, gamma, beta, rmean, rvar, bnc, C, training);
+  k_bn_finalize<<<(C + 127) / 128, 128, 0, st>>>(stats, (double)count, gamma, beta, rmean, rvar, bnc, C, training, nullptr);
   AE_LAUNCH_CHECK();
   return 0;
 }
@@ -49,18 +50,29 @@ int bn_finalize(const double* stats, int64_t count, const float* gamma, const fl
 int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta,
                   int C, cudaStream_t st);
 
+__global__ void k_bn_bwd_reduce(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+                                float* __restrict__ bnc, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                                float* __restrict__ dzero);
+
 int run_bn_job(const BnJob& j, cudaStream_t st) {
-  if (j.kind == BN_JOB_FINALIZE)
-    return bn_finalize(j.stats, (int64_t)j.count, j.gamma, j.beta, j.rmean, j.rvar, j.bnc, j.C, j.training, st);
-  if (j.kind == BN_JOB_BWD) return bn_bwd_reduce(j.stats, (int64_t)j.count, j.gamma, j.bnc, j.dgamma, j.dbeta, j.C, st);
+  if (j.kind == BN_JOB_FINALIZE) {
+    AE_CHECK(j.training || (j.rmean && j.rvar), "bn job: eval mode needs running statistics");
+    k_bn_finalize<<<(j.C + 127) / 128, 128, 0, st>>>(j.stats, j.count, j.gamma, j.beta, j.rmean, j.rvar, j.bnc, j.C, j.training, j.nbt);
+    AE_LAUNCH_CHECK();
+  } else if (j.kind == BN_JOB_BWD) {
+    k_bn_bwd_reduce<<<(j.C + 127) / 128, 128, 0, st>>>(j.stats, j.count, j.gamma, j.bnc, j.dgamma, j.dbeta, j.C, j.dzero);
+    AE_LAUNCH_CHECK();
+  }
   return 0;
 }
 
 // dy = A*dz + B*(y - mean) + C with  A = gamma*rstd,  B = -A*rstd*S2/M,  C = -A*S1/M
 __global__ void k_bn_bwd_reduce(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
-                                float* __restrict__ bnc, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+                                float* __restrict__ bnc, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                                float* __restrict__ dzero) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (dzero) dzero[c] = 0.f;
   const double s1 = stats[c], s2 = stats[C + c];
   const double rstd = (double)bnc[AE_BNC_RSTD * C + c];
   const double a = (double)gamma[c] * rstd;
@@ -75,7 +87,7 @@ __global__ void k_bn_bwd_reduce(const double* __restrict__ stats, double count, 
 
 int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta,
                   int C, cudaStream_t st) {
-  k_bn_bwd_reduce<<<(C + 127) / 128, 128, 0, st>>>(stats, (double)count, gamma, bnc, dgamma, dbeta, C);
+  k_bn_bwd_reduce<<<(C + 127) / 128, 128, 0, st>>>(stats, (double)count, gamma, bnc, dgamma, dbeta, C, nullptr);
   AE_LAUNCH_CHECK();
   return 0;
 }

@@ -15,7 +15,7 @@ int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias
                int batch, cudaStream_t st);
 size_t thin_wgrad_workspace_bytes(int batch);
 int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
-                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st);
+                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st, int phase);
 int thin_tc_gather_fwd(const Operand& thin, const float* w, const Epilogue& epi, float* out, int batch, int nsplit, cudaStream_t st);
 int thin_tc_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes, int batch,
                   int nsplit, cudaStream_t st);
@@ -42,11 +42,6 @@ int head_fused_step(const float* z, const int64_t* labels, const float* w1, cons
                     int B, int L, int C, cudaStream_t st_main, cudaStream_t st_finish, int phase);
 int head_backward_small(const float* dlogits, const float* w2, const float* hid_pre, float* dhid, float* dw2, float* db2,
                         int B, int H, int C, cudaStream_t st);
-
-__global__ void k_inc_i64(int64_t* p, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] += 1;
-}
 
 static inline int64_t pad4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 
@@ -314,6 +309,14 @@ static int join_side(ae_engine* e, cudaStream_t st) {
   return 0;
 }
 
+// split-K of the two 4096-deep dense GEMMs: enough CTAs to fill the chip at small batches, fewer partials at large ones
+static int fc_split_for(const ae_engine* e, int batch) {
+  const int mtiles = (batch + 63) / 64;
+  int s = e->fc_split;
+  while (s > 1 && mtiles * s > 4 * 148) s >>= 1;
+  return s;
+}
+
 static int check_batch(const ae_engine* e, int batch) {
   AE_CHECK(e->ws != nullptr, "engine: workspace not bound (ae_engine_bind_workspace)");
   AE_CHECK(batch >= 1 && batch <= e->Bmax, "engine: batch %d outside [1, max_batch=%d]", batch, e->Bmax);
@@ -331,14 +334,18 @@ static BnJob bn_fwd_job(const Part& P, int l, int batch, int training) {
   j.kind = BN_JOB_FINALIZE; j.stats = b.stats_f; j.count = (double)batch * (double)b.count_per_image;
   j.gamma = P.P(b.gamma); j.beta = P.P(b.beta); j.rmean = P.rmean(l); j.rvar = P.rvar(l); j.bnc = b.bnc;
   j.dgamma = nullptr; j.dbeta = nullptr; j.C = b.C; j.training = training;
+  j.nbt = (training && P.steps) ? P.steps + l : nullptr;     // num_batches_tracked += 1 rides on the layer's finalize job
+  j.dzero = nullptr;
   return j;
 }
-static BnJob bn_bwd_job(const Part& P, int l, int batch) {
+// `dzero`: gradient slot of the bias in front of this BatchNorm (exactly zero: the batch mean removes it)
+static BnJob bn_bwd_job(const Part& P, int l, int batch, float* dzero) {
   const BN& b = P.bn[l];
   BnJob j{};
   j.kind = BN_JOB_BWD; j.stats = b.stats_b; j.count = (double)batch * (double)b.count_per_image;
   j.gamma = P.P(b.gamma); j.beta = nullptr; j.rmean = nullptr; j.rvar = nullptr; j.bnc = b.bnc;
   j.dgamma = P.G(b.gamma); j.dbeta = P.G(b.beta); j.C = b.C; j.training = 1;
+  j.nbt = nullptr; j.dzero = dzero;
   return j;
 }
 
@@ -527,7 +534,6 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
   AE_CHECK(!training || P.running, "ae_encoder_forward: training mode needs BatchNorm running buffers");
   if (training) {
     AE_CUDA(cudaMemsetAsync(P.bn[0].stats_f, 0, (char*)(P.bn[3].stats_b + 2 * P.bn[3].C) - (char*)P.bn[0].stats_f, st));
-    if (P.steps) { k_inc_i64<<<1, 32, 0, st>>>(P.steps, 4); AE_LAUNCH_CHECK(); }
   }
   // Eval mode on the tcgen05 path: the BatchNorm coefficients come from the running statistics, so they are known before
   // the first kernel runs and every layer's epilogue can emit the next layer's operand directly -- split-bf16 planes of
@@ -573,9 +579,9 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
     r.family = FAM_DENSE; r.M = batch; r.N = e->L; r.K = 4096;
     r.A = bnrelu_operand(e->y[3], P.bn[3].bnc, 256);
     r.Bp = e->encfc_fwd; r.epi = store_epilogue(); r.out = nullptr;
-    r.splitK = e->fc_split; r.partial = e->partial;
+    r.splitK = fc_split_for(e, batch); r.partial = e->partial;
     AE_TRY(simt_rowgemm(r, st));
-    AE_TRY(reduce_partials(e->partial, e->fc_split, (int64_t)batch * e->L, P.P(17), e->L, nullptr, e->z, st));
+    AE_TRY(reduce_partials(e->partial, r.splitK, (int64_t)batch * e->L, P.P(17), e->L, nullptr, e->z, st));
     if (z && z != e->z) AE_CUDA(cudaMemcpyAsync(z, e->z, (size_t)batch * e->L * 4, cudaMemcpyDeviceToDevice, st));
   }
   e->last_x = x;
@@ -623,13 +629,12 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     Geom g = m.g; g.B = batch;
     const Operand a_big = bnrelu_operand(e->y[i], bin.bnc, bin.C);                          // planes: ae_pl[i] (forward)
     const Operand dy_small = bnbwd_operand(e->dzy[i + 1], e->y[i + 1], bout.bnc, bout.C);   // planes: dy_pl (now)
-    const BnJob job = bn_bwd_job(P, i + 1, batch);            // backward coefficients of the output BatchNorm
+    const BnJob job = bn_bwd_job(P, i + 1, batch, P.G(m.b));  // backward coefficients of the output BatchNorm (+ zero bias gradient)
     if (!e->simt) AE_TRY(tma_split_operand(dy_small, (int64_t)Mrows * m.g.Cs, e->dy_pl, e->nsplit, &job, st));
     else AE_TRY(run_bn_job(job, st));
     // the weight gradient runs beside the data gradient (both only read the dy planes)
     if (!e->simt) AE_TRY(fork_side(e, st));
     AE_TRY(run_conv_wgrad(e, g, a_big, dy_small, e->ae_pl[i], e->dy_pl, P.G(m.w), e->simt ? st : e->side));
-    AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cs * 4, st));   // bias feeding a training BN: exact zero gradient
     RowGemm r{};
     r.family = FAM_DGRAD; r.g = g; r.M = Mrows; r.N = m.g.Cb; r.K = 0;
     r.Bp = (const float*)m.pk_dgrad;
@@ -638,8 +643,7 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     AE_TRY(run_rowgemm(e, r, dy_small, e->dy_pl, false, 0, m.pk_dgrad, nullptr, st));
     if (!e->simt) AE_TRY(join_side(e, st));
   }
-  AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch), st));
-  AE_CUDA(cudaMemsetAsync(P.G(1), 0, 32 * 4, st));
+  AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch, P.G(1)), st));
   if (!e->defer_conv1_wgrad) AE_TRY(conv1_wgrad(e, batch, st));
   return 0;
 }
@@ -655,7 +659,6 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
   AE_CHECK(!training || P.running, "ae_decoder_forward: training mode needs BatchNorm running buffers");
   if (training) {
     AE_CUDA(cudaMemsetAsync(P.bn[0].stats_f, 0, (char*)(e->sse + 2) - (char*)P.bn[0].stats_f, st));
-    if (P.steps) { k_inc_i64<<<1, 32, 0, st>>>(P.steps, 3); AE_LAUNCH_CHECK(); }
   } else {
     AE_CUDA(cudaMemsetAsync(e->sse, 0, 16, st));
   }
@@ -717,9 +720,19 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
   const int L = e->L;
   // convT4 (32 -> 3)
   // (thin_tc_bwd_fused: same speed as the fp32 CUDA-core kernel)
-  AE_TRY(thin_bwd_fused(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), thin_up, P.P(14),
-                        relubwd_epilogue(e->t[2], P.bn[2].bnc, P.bn[2].stats_b, 32), e->dzt[2], P.G(14), P.G(15), e->partial,
-                        e->partial_bytes, batch, st));
+  {
+    const Operand wide = bnrelu_operand(e->t[2], P.bn[2].bnc, 32);
+    const Epilogue ep = relubwd_epilogue(e->t[2], P.bn[2].bnc, P.bn[2].stats_b, 32);
+    if (e->simt) {
+      AE_TRY(thin_bwd_fused(wide, thin_up, P.P(14), ep, e->dzt[2], P.G(14), P.G(15), e->partial, e->partial_bytes, batch, st, 0));
+    } else {
+      // the reduce of the weight-gradient partials leaves the data-gradient path: it runs on the side branch, ahead of
+      // the next layer's weight gradient (same stream, so the shared partial buffer is free again when that one starts)
+      AE_TRY(thin_bwd_fused(wide, thin_up, P.P(14), ep, e->dzt[2], P.G(14), P.G(15), e->partial, e->partial_bytes, batch, st, 1));
+      AE_TRY(fork_side(e, st));
+      AE_TRY(thin_bwd_fused(wide, thin_up, P.P(14), ep, e->dzt[2], P.G(14), P.G(15), e->partial, e->partial_bytes, batch, e->side, 2));
+    }
+  }
   for (int i = 2; i >= 0; --i) {
     MidLayer& m = e->dec_mid[i];
     BN& bout = P.bn[i];  // BN after this layer's output (big image)
@@ -728,12 +741,11 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     if (i == 0) small.C = m.g.Cs;                                                   // planes: h_pl / ad_pl[i-1] (forward)
     const Operand dy_big = bnbwd_operand(e->dzt[i], e->t[i], bout.bnc, bout.C);     // planes: dy_pl (now)
     Geom g = m.g; g.B = batch;
-    const BnJob job = bn_bwd_job(P, i, batch);
+    const BnJob job = bn_bwd_job(P, i, batch, P.G(m.b));
     if (!e->simt) AE_TRY(tma_split_operand(dy_big, (int64_t)Mrows * 4 * m.g.Cb, e->dy_pl, e->nsplit, &job, st));
     else AE_TRY(run_bn_job(job, st));
     if (!e->simt) AE_TRY(fork_side(e, st));
     AE_TRY(run_conv_wgrad(e, g, dy_big, small, e->dy_pl, i == 0 ? e->h_pl : e->ad_pl[i - 1], P.G(m.w), e->simt ? st : e->side));
-    AE_CUDA(cudaMemsetAsync(P.G(m.b), 0, (size_t)m.g.Cb * 4, st));
     RowGemm r{};
     r.family = FAM_FPROP; r.g = g; r.M = Mrows; r.N = m.g.Cs; r.K = 9 * m.g.Cb;
     r.Bp = (const float*)m.pk_fwd;
@@ -755,9 +767,9 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = L; r.K = 4096;
     r.A = raw_operand(e->dh); r.Bp = e->decfc_bwd; r.epi = store_epilogue(); r.out = nullptr;
-    r.splitK = e->fc_split; r.partial = e->partial;
+    r.splitK = fc_split_for(e, batch); r.partial = e->partial;
     AE_TRY(simt_rowgemm(r, st));
-    AE_TRY(reduce_partials(e->partial, e->fc_split, (int64_t)batch * L, nullptr, 0, dz_addend, dz, st));
+    AE_TRY(reduce_partials(e->partial, r.splitK, (int64_t)batch * L, nullptr, 0, dz_addend, dz, st));
     if (par) AE_TRY(join_side(e, st));
   }
   return 0;
@@ -828,9 +840,12 @@ int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int bat
                          loss_out, e->sse, numel, alpha, e->head_partial, e->head_counter, batch, e->L, e->NC,
                          par ? e->side : st, st, 1));
   AE_TRY(decoder_forward_impl(e, e->z, batch, 1, nullptr, x, st));
-  if (par) AE_TRY(join_side(e, st));
+  // the head's reduction (parameter gradients + the loss, which needs the decoder's squared error) stays on the side
+  // branch behind the decoder forward; the decoder backward joins that branch before anything reads dz_head
+  if (par) AE_TRY(fork_side(e, st));
   AE_TRY(head_fused_step(e->z, labels, H.P(0), H.P(1), H.P(2), H.P(3), e->logits, e->dz_head, H.G(0), H.G(1), H.G(2), H.G(3),
-                         loss_out, e->sse, numel, alpha, e->head_partial, e->head_counter, batch, e->L, e->NC, st, st, 2));
+                         loss_out, e->sse, numel, alpha, e->head_partial, e->head_counter, batch, e->L, e->NC,
+                         par ? e->side : st, par ? e->side : st, 2));
   Operand up;
   up.src = x; up.src2 = e->xhat; up.bnc = nullptr; up.scalar = (float)(2.0 * (double)alpha / numel);
   up.mode = AE_OP_SIGMOID_BWD; up.C = 1;

@@ -416,15 +416,24 @@ int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias
 
 // Fused backward of the thin transposed convolution (NB:628): weight / bias gradient and the data gradient
 // (gather with the ReLU-backward epilogue) from one pass over the thin operand.
+// phase 0: both launches on `st`; phase 1: the fused kernel only; phase 2: only the fixed-order reduce of its per-CTA
+// partials (the engine runs it on a parallel graph branch: nothing on the data-gradient path reads dw / dbias).
 int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
-                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st) {
+                   float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st, int phase) {
   AE_TRY(check_thin_operand(thin));
   AE_TRY(check_wide_operand(wide));
   int blocks = 0;
   AE_CHECK(bytes >= (size_t)thin_blocks(batch) * TW_PART * sizeof(float), "thin_bwd_fused: workspace too small");
-  AE_TRY((launch_thin<true, true>(thin, wide, w, epi, out_wide, static_cast<float*>(partials), batch, st, &blocks)));
-  k_thin_wgrad_reduce<<<(867 + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(partials), blocks, dw, dbias);
-  AE_LAUNCH_CHECK();
+  if (phase == 0 || phase == 1) {
+    AE_TRY((launch_thin<true, true>(thin, wide, w, epi, out_wide, static_cast<float*>(partials), batch, st, &blocks)));
+  } else {
+    const ThinStage L = thin_stage_layout(thin.mode, wide.mode, true);
+    AE_TRY(resident_blocks(k_thin<true, true>, sizeof(float) * (2 * (size_t)L.floats + 27 * 32 + 8 * 32), batch, &blocks));
+  }
+  if (phase == 0 || phase == 2) {
+    k_thin_wgrad_reduce<<<(867 + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(partials), blocks, dw, dbias);
+    AE_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(256) k_split_operand(Operand op, int64_t n8, i
         const float shift = job.beta[c] - (float)mean * scale;
         sc[0][c] = scale; sc[1][c] = shift;
         if (blockIdx.x == 0) {
+          if (c == 0 && job.training && job.nbt) *job.nbt += 1;
           if (job.training && job.rmean) {
             const double unb = job.count > 1.0 ? var * job.count / (job.count - 1.0) : var;
             job.rmean[c] = (float)(0.9 * (double)job.rmean[c] + 0.1 * mean);
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) k_split_operand(Operand op, int64_t n8, i
           job.bnc[AE_BNC_A * C + c] = fa; job.bnc[AE_BNC_B * C + c] = fb; job.bnc[AE_BNC_C * C + c] = fk;
           if (job.dgamma) job.dgamma[c] = (float)s2;
           if (job.dbeta) job.dbeta[c] = (float)s1;
+          if (job.dzero) job.dzero[c] = 0.f;
         }
       } else if (op.mode == AE_OP_BNRELU) {
         sc[0][c] = op.bnc[AE_BNC_SCALE * C + c]; sc[1][c] = op.bnc[AE_BNC_SHIFT * C + c];

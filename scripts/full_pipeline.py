@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""BASELINE configs[2]: the full two-stage pipeline on a synthetic 27,000-image EuroSAT-shaped set (10 classes x 2,700,
+split 18,900 / 4,050 / 4,050 by the reference's rule NB:306-308), entirely on the device.
+
+  python scripts/full_pipeline.py [--precision bf16] [--ae-epochs 20] [--mlp-epochs 30] [--ae-batch 64]
+
+Prints one JSON line: per-stage seconds, epochs run, accuracies.  The images are class-structured (per-class colour mean
++ low-frequency pattern + noise) so accuracy is meaningful; they are generated on the device.
+"""
+import argparse, json, math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ae_b200
+
+
+def structured_u8(n_per_class, seed, dev):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    labels = torch.arange(10, device=dev).repeat_interleave(n_per_class)
+    n = labels.numel()
+    gc = torch.Generator().manual_seed(424242)
+    means = (torch.rand(10, 3, generator=gc) * 0.6 + 0.2).to(dev)
+    freq = (torch.rand(10, 2, generator=gc) * 2.5 + 0.5).to(dev)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, 64, device=dev), torch.linspace(0, 1, 64, device=dev), indexing="ij")
+    phase = torch.rand(n, 2, device=dev, generator=g) * 2 * math.pi
+    img = torch.empty(n, 64, 64, 3, device=dev)
+    for c in range(3):
+        pat = 0.15 * torch.sin(2 * math.pi * freq[labels, 0, None, None] * yy + phase[:, 0, None, None] + c) * \
+            torch.cos(2 * math.pi * freq[labels, 1, None, None] * xx + phase[:, 1, None, None])
+        img[..., c] = means[labels, c, None, None] + pat
+    img += 0.03 * torch.randn(img.shape, device=dev, generator=g)
+    u8 = (img.clamp(0, 1) * 255).round().to(torch.uint8)
+    perm = torch.randperm(n, device=dev, generator=g)
+    return u8[perm].contiguous(), labels[perm].contiguous()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--ae-epochs", type=int, default=20)
+    ap.add_argument("--mlp-epochs", type=int, default=30)
+    ap.add_argument("--ae-batch", type=int, default=64)       # the reference's batch size (NB:418)
+    ap.add_argument("--per-class", type=int, default=2700)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    imgs, labels = structured_u8(a.per_class, 0, dev)
+    n = imgs.shape[0]
+    n_tr, n_va = int(0.7 * n), int(0.15 * n)                  # NB:306-308
+    mk = lambda s, e: ae_b200.DeviceDataset(imgs[s:e], labels[s:e])
+    tr, va, te = mk(0, n_tr), mk(n_tr, n_tr + n_va), mk(n_tr + n_va, n)
+    torch.manual_seed(0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    res = ae_b200.pipeline.run_pipeline(tr, va, te, alpha=35.0, ae_lr=5e-3, mlp_lr=1e-4, ae_epochs=a.ae_epochs, ae_patience=15,
+                                        mlp_epochs=a.mlp_epochs, ae_batch=a.ae_batch, precision=a.precision, generator=g, seed=2)
+    ae_imgs = res["ae"]["epochs"] * (len(tr) + len(va))
+    print(json.dumps({"config": "full pipeline, synthetic class-structured set", "images": n, "splits": [len(tr), len(va), len(te)],
+                      "precision": a.precision, "ae_batch": a.ae_batch, "ae_epochs_run": res["ae"]["epochs"],
+                      "mlp_epochs": a.mlp_epochs, "seconds": res["seconds"],
+                      "ae_images_per_s": ae_imgs / res["seconds"]["autoencoder"],
+                      "ae_final_train_loss": res["ae"]["train_curve"][-1], "ae_best_val_loss": res["ae"]["best_val_loss"],
+                      "mlp_best_val_acc": res["mlp"]["best_val_acc"], "test_acc": res["test_acc"]}))
+
+
+if __name__ == "__main__":
+    main()

@@ -156,3 +156,47 @@ def test_fit_autoencoder_early_stopping_runs_on_device():
     assert 1 <= res["epochs"] <= 4 and len(res["val_curve"]) == res["epochs"]
     assert all(np.isfinite(v) for v in res["train_curve"] + res["val_curve"])
     assert res["train_curve"][-1] < res["train_curve"][0]          # it learns
+
+
+def _structured_u8(n_per_class, seed):
+    labels = torch.arange(10).repeat_interleave(n_per_class)
+    x = seeded.structured_images(labels, seed)                       # [N,3,64,64] fp32 in [0,1]
+    u8 = (x * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    perm = torch.from_numpy(np.random.RandomState(seed).permutation(labels.numel()))
+    return u8[perm], labels[perm]
+
+
+def test_mlp_eval_epoch_matches_oracle():
+    d = gu.dev()
+    clf = ae_b200.MLP(64, 10).to(d)
+    st = gu.load_mlp(clf, 5)
+    clf = clf.to(d).eval()
+    rs = np.random.RandomState(2)
+    X = torch.from_numpy(rs.standard_normal((5000, 64)).astype(np.float32))
+    y = torch.from_numpy(rs.randint(0, 10, size=5000))
+    loss, acc = ae_b200.fit.eval_epoch_mlp(clf, X.to(d), y.to(d), batch_size=2048)      # 2048, 2048, 904
+    with torch.no_grad():
+        logits = tp.mlp_forward(st, X, False)
+    ref_loss = float(torch.nn.functional.cross_entropy(logits.double(), y))
+    ref_acc = float((logits.argmax(1) == y).double().mean())
+    assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss) and abs(acc - ref_acc) <= 2 / 5000
+
+
+def test_full_pipeline_on_class_structured_data():
+    """BASELINE configs[2] at test scale: AE training with early stopping -> frozen encoder -> latents on the device ->
+    MLP, all through the device-side loaders.  The classes are separable, so the pipeline must learn them."""
+    d = gu.dev()
+    tr = ae_b200.DeviceDataset(*_structured_u8(60, 1), device=d)
+    va = ae_b200.DeviceDataset(*_structured_u8(15, 2), device=d)
+    te = ae_b200.DeviceDataset(*_structured_u8(15, 3), device=d)
+    torch.manual_seed(0)
+    g = torch.Generator(device=d).manual_seed(0)
+    res = ae_b200.pipeline.run_pipeline(tr, va, te, alpha=35.0, ae_lr=2e-3, mlp_lr=5e-3, ae_epochs=6, ae_patience=3,
+                                        mlp_epochs=12, generator=g, seed=4)
+    assert res["ae"]["epochs"] >= 1 and res["ae"]["train_curve"][-1] < res["ae"]["train_curve"][0]
+    assert res["mlp"]["best_val_acc"] > 0.6 and res["test_acc"] > 0.6, (res["mlp"]["best_val_acc"], res["test_acc"])
+    assert not any(p.requires_grad for p in res["model"].enc.parameters())
+    # the latents the MLP saw are the encoder's: predict through the public inference path and compare accuracies
+    x = ae_b200.EvalTransform()(te.images)
+    _, _, am = ae_b200.encode_predict(res["model"].enc, res["clf"], x)
+    assert abs(float((am == te.labels).float().mean()) - res["test_acc"]) <= 1e-6
