@@ -63,7 +63,8 @@ struct Epilogue {
   const float* bnc;
   double* stats;
   int C;             // channels of the BN this epilogue feeds (channel = n % C)
-  int nsplit;        // BNRELU_SPLIT: bf16 planes written (2 = hi + lo, 1 = hi only)
+  int nsplit;        // BNRELU_SPLIT / planes: bf16 planes written (2 = hi + lo, 1 = hi only)
+  void* planes;      // dense row GEMM, STORE mode: also (out == NULL: only) write the result as split-bf16 planes [nsplit][M*N]
 };
 
 // BatchNorm coefficient job a consumer kernel can run in its prologue instead of a separate launch:
@@ -119,24 +120,24 @@ inline Operand bnbwd_operand(const float* dz, const float* y, const float* bnc, 
 }
 inline Epilogue make_epilogue(const ae_epilogue_t* e, int C) {
   Epilogue r;
-  if (!e) { r.mode = AE_EPI_STORE; r.bias = nullptr; r.y = nullptr; r.bnc = nullptr; r.stats = nullptr; r.C = C; r.nsplit = 2; return r; }
-  r.mode = e->mode; r.bias = e->bias; r.y = e->y; r.bnc = e->bnc; r.stats = e->stats; r.C = C; r.nsplit = 2;
+  if (!e) { r.mode = AE_EPI_STORE; r.bias = nullptr; r.y = nullptr; r.bnc = nullptr; r.stats = nullptr; r.C = C; r.nsplit = 2; r.planes = nullptr; return r; }
+  r.mode = e->mode; r.bias = e->bias; r.y = e->y; r.bnc = e->bnc; r.stats = e->stats; r.C = C; r.nsplit = 2; r.planes = nullptr;
   return r;
 }
 inline Epilogue store_epilogue(const float* bias = nullptr) {
-  Epilogue r; r.mode = AE_EPI_STORE; r.bias = bias; r.y = nullptr; r.bnc = nullptr; r.stats = nullptr; r.C = 1; r.nsplit = 2;
+  Epilogue r; r.mode = AE_EPI_STORE; r.bias = bias; r.y = nullptr; r.bnc = nullptr; r.stats = nullptr; r.C = 1; r.nsplit = 2; r.planes = nullptr;
   return r;
 }
 inline Epilogue bias_stats_epilogue(const float* bias, double* stats, int C) {
-  Epilogue r; r.mode = AE_EPI_BIAS_STATS; r.bias = bias; r.y = nullptr; r.bnc = nullptr; r.stats = stats; r.C = C; r.nsplit = 2;
+  Epilogue r; r.mode = AE_EPI_BIAS_STATS; r.bias = bias; r.y = nullptr; r.bnc = nullptr; r.stats = stats; r.C = C; r.nsplit = 2; r.planes = nullptr;
   return r;
 }
 inline Epilogue bnrelu_split_epilogue(const float* bias, const float* bnc, int C, int nsplit) {
-  Epilogue r; r.mode = AE_EPI_BNRELU_SPLIT; r.bias = bias; r.y = nullptr; r.bnc = bnc; r.stats = nullptr; r.C = C; r.nsplit = nsplit;
+  Epilogue r; r.mode = AE_EPI_BNRELU_SPLIT; r.bias = bias; r.y = nullptr; r.bnc = bnc; r.stats = nullptr; r.C = C; r.nsplit = nsplit; r.planes = nullptr;
   return r;
 }
 inline Epilogue relubwd_epilogue(const float* y, const float* bnc, double* stats, int C) {
-  Epilogue r; r.mode = AE_EPI_RELUBWD_STATS; r.bias = nullptr; r.y = y; r.bnc = bnc; r.stats = stats; r.C = C; r.nsplit = 2;
+  Epilogue r; r.mode = AE_EPI_RELUBWD_STATS; r.bias = nullptr; r.y = y; r.bnc = bnc; r.stats = stats; r.C = C; r.nsplit = 2; r.planes = nullptr;
   return r;
 }
 

@@ -126,6 +126,7 @@ struct ae_engine {
   // data-parallel step being captured: gradient exchange interleaved with the backward pass
   ae_dp_comm_t* step_comm = nullptr;
   bool defer_conv1_wgrad = false;     // the captured step runs conv1's weight gradient beside Adam + re-pack of everything else
+  bool stats_cleared = false;         // the fused step zeroed every statistic accumulator in one memset: the parts skip theirs
   // pointers remembered between forward and backward
   const float* last_x = nullptr;
   const float* last_z_dec = nullptr;
@@ -532,7 +533,7 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
   AE_TRY(check_part(e, AE_PART_ENC, false));
   Part& P = e->part[AE_PART_ENC];
   AE_CHECK(!training || P.running, "ae_encoder_forward: training mode needs BatchNorm running buffers");
-  if (training) {
+  if (training && !e->stats_cleared) {
     AE_CUDA(cudaMemsetAsync(P.bn[0].stats_f, 0, (char*)(P.bn[3].stats_b + 2 * P.bn[3].C) - (char*)P.bn[0].stats_f, st));
   }
   // Eval mode on the tcgen05 path: the BatchNorm coefficients come from the running statistics, so they are known before
@@ -658,7 +659,7 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
   Part& P = e->part[AE_PART_DEC];
   AE_CHECK(!training || P.running, "ae_decoder_forward: training mode needs BatchNorm running buffers");
   if (training) {
-    AE_CUDA(cudaMemsetAsync(P.bn[0].stats_f, 0, (char*)(e->sse + 2) - (char*)P.bn[0].stats_f, st));
+    if (!e->stats_cleared) AE_CUDA(cudaMemsetAsync(P.bn[0].stats_f, 0, (char*)(e->sse + 2) - (char*)P.bn[0].stats_f, st));
   } else {
     AE_CUDA(cudaMemsetAsync(e->sse, 0, 16, st));
   }
@@ -670,6 +671,9 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
     r.family = FAM_DENSE; r.M = batch; r.N = 4096; r.K = e->L;
     r.A = raw_operand(z); r.Bp = e->decfc_fwd; r.epi = store_epilogue(e->decfc_bias);
     r.out = e->h; r.splitK = 1;
+    if (!e->simt) {       // the only reader is ConvTranspose2d(256,128) on tensor cores: write its operand planes, not fp32
+      r.out = nullptr; r.epi.planes = e->h_pl; r.epi.nsplit = e->nsplit;
+    }
     AE_TRY(simt_rowgemm(r, st));
   }
   for (int i = 0; i < 3; ++i) {
@@ -685,7 +689,6 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
     r.out = e->t[i]; r.splitK = 1;
     if (fused_eval) {
       // convT1 / convT2 emit the next layer's operand planes; convT3 stores fp32 for the 3-channel scatter kernel
-      if (i == 0) AE_TRY(tma_split_operand(a, (int64_t)r.M * m.g.Cs, e->h_pl, e->nsplit, nullptr, st));
       if (i < 2) { r.epi = bnrelu_split_epilogue(P.P(m.b), bout.bnc, bout.C, e->nsplit); r.out = (float*)e->ad_pl[i]; }
       r.A = split_operand(i == 0 ? e->h_pl : e->ad_pl[i - 1], m.g.Cs);
       AE_TRY(tma_rowgemm(r, m.pk_dgrad, e->nsplit, st));
@@ -693,7 +696,7 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
     }
     BnJob job{};
     if (i > 0) job = bn_fwd_job(P, i - 1, batch, training);
-    AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], true, (int64_t)r.M * m.g.Cs, m.pk_dgrad,
+    AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], i > 0 || e->simt, (int64_t)r.M * m.g.Cs, m.pk_dgrad,
                        i > 0 ? &job : nullptr, st));
   }
   if (!fused_eval) AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
@@ -828,7 +831,14 @@ int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int bat
                   ae_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   AE_CHECK(e && x && labels && loss_out, "ae_train_step: null argument");
-  AE_TRY(ae_encoder_forward(e, x, batch, 1, nullptr, stream));
+  AE_TRY(check_batch(e, batch));
+  // every BatchNorm statistic accumulator of both parts + the squared-error accumulator: one memset for the whole step
+  AE_CUDA(cudaMemsetAsync(e->stats_base, 0, e->stats_bytes, st));
+  struct Cleared { bool& f; explicit Cleared(bool& b) : f(b) { f = true; } ~Cleared() { f = false; } };
+  {
+    Cleared guard(e->stats_cleared);
+    AE_TRY(ae_encoder_forward(e, x, batch, 1, nullptr, stream));
+  }
   const double numel = (double)batch * 12288.0;
   AE_TRY(check_part(e, AE_PART_HEAD, true));
   Part& H = e->part[AE_PART_HEAD];
@@ -839,7 +849,10 @@ int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int bat
   AE_TRY(head_fused_step(e->z, labels, H.P(0), H.P(1), H.P(2), H.P(3), e->logits, e->dz_head, H.G(0), H.G(1), H.G(2), H.G(3),
                          loss_out, e->sse, numel, alpha, e->head_partial, e->head_counter, batch, e->L, e->NC,
                          par ? e->side : st, st, 1));
-  AE_TRY(decoder_forward_impl(e, e->z, batch, 1, nullptr, x, st));
+  {
+    Cleared guard(e->stats_cleared);
+    AE_TRY(decoder_forward_impl(e, e->z, batch, 1, nullptr, x, st));
+  }
   // the head's reduction (parameter gradients + the loss, which needs the decoder's squared error) stays on the side
   // branch behind the decoder forward; the decoder backward joins that branch before anything reads dz_head
   if (par) AE_TRY(fork_side(e, st));

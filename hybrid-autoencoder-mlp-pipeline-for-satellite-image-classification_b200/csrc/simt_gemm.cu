@@ -156,7 +156,20 @@ __global__ void __launch_bounds__(256) k_rowgemm(RowGemm p) {
           s2[j] += v[j] * ((yv[j] - mu[j]) * rs[j]);
         }
       }
-      *reinterpret_cast<float4*>(p.out + row + n) = make_float4(v[0], v[1], v[2], v[3]);
+      if (p.out) *reinterpret_cast<float4*>(p.out + row + n) = make_float4(v[0], v[1], v[2], v[3]);
+      if (e.planes) {     // the consumer is a tcgen05 GEMM: hand it its operand planes directly (no separate split pass)
+        __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(e.planes);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(pl + row + n) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        if (e.nsplit == 2) {
+          float lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+          __nv_bfloat162 l0 = __floats2bfloat162_rn(lo[0], lo[1]), l1 = __floats2bfloat162_rn(lo[2], lo[3]);
+          *reinterpret_cast<uint2*>(pl + (size_t)p.M * p.N + row + n) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+        }
+      }
     }
   }
   if (e.mode != AE_EPI_STORE && e.stats) {
@@ -176,6 +189,9 @@ __global__ void __launch_bounds__(256) k_rowgemm(RowGemm p) {
 int simt_rowgemm(const RowGemm& p, cudaStream_t st) {
   AE_CHECK(p.N % 4 == 0, "simt_rowgemm: N=%d must be a multiple of 4", p.N);
   AE_CHECK(p.epi.mode != AE_EPI_BNRELU_SPLIT, "simt_rowgemm: the split-bf16 epilogue exists on the tcgen05 path only");
+  AE_CHECK(p.epi.planes == nullptr || (p.family == FAM_DENSE && p.epi.mode == AE_EPI_STORE && p.splitK <= 1),
+           "simt_rowgemm: operand planes can only be written by a dense GEMM with the plain store epilogue");
+  AE_CHECK(p.out != nullptr || p.epi.planes != nullptr || p.splitK > 1, "simt_rowgemm: no output");
   dim3 grid((p.M + 63) / 64, (p.N + 63) / 64, 1);
   if (p.family == FAM_DGRAD) {
     AE_CHECK(p.g.Cs % 16 == 0, "simt_rowgemm: Cs=%d must be a multiple of 16", p.g.Cs);
