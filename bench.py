@@ -343,7 +343,7 @@ def run_ours(args):
         line["roofline"] = roof
     if infer is not None:
         line["inference"] = infer
-    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+    if rank == 0 and not args.no_cpu_baseline and world == 1:      # N=1 only: other ranks' spin-waits would share the host cores
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         n = 12
