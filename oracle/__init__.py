@@ -8,6 +8,8 @@ Parity pin: the reference ships no tests or golden vectors
 oracle is pinned against the reference itself: ``oracle/make_golden.py`` executes the
 reference's own notebook cells (NB:499-525, NB:607-635, NB:685-702, NB:2970-2987 and the
 literal train-step lines NB:2652-2654 / NB:2676-2684) in this container and commits their
-outputs under ``tests/golden/``; ``tests/test_oracle_pin.py`` checks this restatement and
-the plain-C restatement (``oracle/c/ae_oracle.c``) against those vectors.
+outputs under ``tests/golden/``; ``tests/test_oracle_pin.py`` checks this restatement against
+those vectors.  The input transforms (NB:361-368, NB:386-395) are restated in
+``oracle/augment_port.py`` and pinned the same way (``oracle/make_golden_augment.py`` runs the
+reference's own torchvision ``Compose`` objects).
 """
