@@ -19,6 +19,7 @@
 //       partial tiles reduced in a fixed order (deterministic).
 //
 // AE_PREC_FP32 issues hi*hi + hi*lo + lo*hi (3 MMAs per k-step, fp32 accumulate): ~2^-17 relative error per product.
+#include <cstdlib>
 #include <mutex>
 
 #include "pack.cuh"
@@ -218,6 +219,11 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr uint32_t TMEM_COLS = 2 * NT;                      // two accumulators
+  // The weight pack is laid out in n-tiles of PK_NT = min(NT, 64) rows, [hi plane][lo plane] per (n-tile, chunk).  A
+  // 128-wide tile takes two of them: their planes are copied side by side so that each plane is 128 contiguous rows.
+  constexpr int PK_NT = NT < 64 ? NT : 64;
+  constexpr int NSUB = NT / PK_NT;
+  constexpr uint32_t PK_PLANE = PK_NT * ROWB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
         const int py = phase >> 1, px = phase & 1;
         const int n0 = m0 >> (g.lHs + g.lWs);
         const int y0 = (m0 & (P - 1)) >> g.lWs;
-        const uint8_t* wsrc = q.wtiles + ((size_t)ntile * q.wchunks + kc_off) * B_BYTES;
+        const uint8_t* wsrc = q.wtiles + ((size_t)ntile * NSUB * q.wchunks + kc_off) * (NSPLIT * PK_PLANE);
         for (int it = 0; it < nkc; ++it, ++gc) {
           const uint32_t s = gc % STAGES, round = gc / STAGES;
           if (round > 0) mbar_wait(empty_bar(s), (round - 1) & 1);
@@ -310,7 +316,16 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
             const int dy = (py && a == 0) ? 1 : 0, dx = (px && b == 0) ? 1 : 0;   // source = (y + dy, x + dx)
             tma_load_5d(a_dst, &q.amap[0], c0, dx, y0 + dy, n0, 0, full_bar(s));
           }
-          bulk_copy_g2s(a_dst + A_BYTES, wsrc + (size_t)it * B_BYTES, B_BYTES, full_bar(s));
+          if (NSUB == 1) {
+            bulk_copy_g2s(a_dst + A_BYTES, wsrc + (size_t)it * B_BYTES, B_BYTES, full_bar(s));
+          } else {
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub)
+#pragma unroll
+              for (int pl = 0; pl < NSPLIT; ++pl)
+                bulk_copy_g2s(a_dst + A_BYTES + pl * B_PLANE + sub * PK_PLANE,
+                              wsrc + ((size_t)sub * q.wchunks + it) * (NSPLIT * PK_PLANE) + pl * PK_PLANE, PK_PLANE, full_bar(s));
+          }
         }
       }
     }
@@ -527,7 +542,8 @@ static int launch_row(const TmaRow& q, dim3 grid, cudaStream_t st) {
     attr_done = true;
   }
   const int tiles = (int)(grid.x * grid.y * grid.z);
-  const int ctas = tiles < 2 * 148 ? tiles : 2 * 148;       // ~97 KB of shared memory per CTA: two CTAs per SM
+  const int per_sm = 2 * (smem + 2048) <= 227 * 1024 ? 2 : 1;   // ~97 KB per CTA: two CTAs per SM; the 128-wide tiles: one
+  const int ctas = tiles < per_sm * 148 ? tiles : per_sm * 148;
   k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES><<<ctas, RG_THREADS, smem, st>>>(q);
   AE_LAUNCH_CHECK();
   return 0;
@@ -544,8 +560,18 @@ int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t s
   q.g = p.g; q.epi = p.epi; q.out = p.out; q.M = p.M; q.N = p.N;
   const Geom& g = p.g;
   pixel_box(g.Hs, g.Ws, TILE_M, &q.bx, &q.by, &q.bn);
-  const int NT = nt_for(p.N);
-  dim3 grid((p.M + TILE_M - 1) / TILE_M, p.N / NT, 1);
+  // 64-wide n-tiles keep the most CTAs busy at training batch sizes; with thousands of m-tiles (inference) a 128-wide tile
+  // halves the A bytes per output and the shared-memory reads per MMA (a 128x64x16 MMA needs 192 B/clk of operands)
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
+  const char* force_env = getenv("AE_B200_FORCE_NT128");       // tests: 1 = wherever the shape allows, -1 = never
+  const int force_nt128 = force_env ? atoi(force_env) : 0;
+  // (bf16 mode issues a third of the MMAs and is bound by the operand loads: two narrower CTAs per SM hide them better,
+  //  measured 6.41 vs 6.32 M images/s)
+  const bool wide = p.N % 128 == 0 && (p.family == FAM_DGRAD || kc_fwd(g.Cb) == 64) &&
+                    (force_nt128 > 0 || (force_nt128 == 0 && nsplit == 2 &&
+                                         (int64_t)m_tiles * (p.N / 128) * (p.family == FAM_DGRAD ? 4 : 1) >= 4 * 148));
+  const int NT = wide ? 128 : nt_for(p.N);
+  dim3 grid(m_tiles, p.N / NT, 1);
   if (p.family == FAM_FPROP) {
     const int KC = kc_fwd(g.Cb);
     q.cpt = g.Cb / KC; q.wchunks = 9 * q.cpt;
@@ -554,6 +580,7 @@ int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t s
         AE_TRY(encode_map(&q.amap[py * 2 + px], p.A.src, g.B, 2 * g.Hs, 2 * g.Ws, g.Cb, nsplit, py, px, 2, 2, g.Hs, g.Ws, KC,
                           q.bx, q.by, q.bn));
     if (KC == 64) {
+      if (NT == 128) return nsplit == 2 ? launch_row<FAM_FPROP, 128, 64, 2, 3>(q, grid, st) : launch_row<FAM_FPROP, 128, 64, 1, 6>(q, grid, st);
       if (NT == 64) return nsplit == 2 ? launch_row<FAM_FPROP, 64, 64, 2, 2>(q, grid, st) : launch_row<FAM_FPROP, 64, 64, 1, 4>(q, grid, st);
       return nsplit == 2 ? launch_row<FAM_FPROP, 32, 64, 2, 2>(q, grid, st) : launch_row<FAM_FPROP, 32, 64, 1, 4>(q, grid, st);
     }
@@ -563,6 +590,7 @@ int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t s
   q.cpt = g.Cs / 64; q.wchunks = 9 * q.cpt;
   AE_TRY(encode_map(&q.amap[0], p.A.src, g.B, g.Hs, g.Ws, g.Cs, nsplit, 0, 0, 1, 1, g.Hs, g.Ws, 64, q.bx, q.by, q.bn));
   grid.z = 4;
+  if (NT == 128) return nsplit == 2 ? launch_row<FAM_DGRAD, 128, 64, 2, 3>(q, grid, st) : launch_row<FAM_DGRAD, 128, 64, 1, 6>(q, grid, st);
   if (NT == 64) return nsplit == 2 ? launch_row<FAM_DGRAD, 64, 64, 2, 2>(q, grid, st) : launch_row<FAM_DGRAD, 64, 64, 1, 4>(q, grid, st);
   return nsplit == 2 ? launch_row<FAM_DGRAD, 32, 64, 2, 2>(q, grid, st) : launch_row<FAM_DGRAD, 32, 64, 1, 4>(q, grid, st);
 }

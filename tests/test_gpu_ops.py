@@ -204,6 +204,50 @@ def test_conv_fused_bnrelu_split_epilogue(shape, family, prec):
 
 
 @pytest.mark.parametrize("prec", gu.PRECISIONS)
+@pytest.mark.parametrize("family", ["fwd", "dgrad"])
+@pytest.mark.parametrize("shape", [(3, 8, 64, 128), (5, 4, 128, 256), (1, 4, 128, 256), (37, 8, 64, 128)])
+def test_conv_wide_n_tiles_match_narrow(shape, family, prec, monkeypatch):
+    """The 128-wide n-tile variant of the row GEMM (chosen for thousands of m-tiles, i.e. inference batches) reads the
+    same weight pack two 64-row n-tiles at a time; every output element accumulates the same products in the same order,
+    so it must reproduce the 64-wide result bit for bit (and the CPU reference within tolerance)."""
+    if "tc" not in gu.BACKENDS:
+        pytest.skip("tcgen05 path only")
+    b, hs, cb, cs = shape
+    rs = np.random.RandomState(hash((shape, family, "wide")) % 2 ** 31)
+    d = gu.dev()
+    w = torch.from_numpy((rs.standard_normal((cs, cb, 3, 3)) / np.sqrt(9 * cb)).astype(np.float32))
+    pf, pd = gu.pack_conv(w.to(d), cs, cb, prec, "tc")
+    g = _geom(b, hs, cb, cs)
+    if family == "fwd":
+        cin, cout, hin, hout = cb, cs, 2 * hs, hs
+    else:
+        cin, cout, hin, hout = cs, cb, hs, 2 * hs
+    a = torch.from_numpy(rs.standard_normal((b, cin, hin, hin)).astype(np.float32))
+    bias = torch.from_numpy(rs.uniform(-0.1, 0.1, cout).astype(np.float32))
+    ad, biasd = gu.nhwc(a).to(d), bias.to(d)
+    op, _keep = gu.conv_operand("tc", prec, cin, ad)
+    fn = gu.lib().ae_conv2d_s2_fwd if family == "fwd" else gu.lib().ae_conv2d_s2_dgrad
+    pk = pf if family == "fwd" else pd
+    outs, stats = [], []
+    for force in ("-1", "1"):
+        monkeypatch.setenv("AE_B200_FORCE_NT128", force)
+        y = torch.full((b, hout, hout, cout), float("nan"), device=d)
+        st = torch.zeros(2 * cout, dtype=torch.float64, device=d)
+        ep = gu.epilogue(_lib.EPI_BIAS_STATS, biasd, None, None, st)
+        _lib.check(fn(C.byref(g), C.byref(op), gu.p(pk), C.byref(ep), gu.p(y), gu.PREC[prec], gu.BACK["tc"], gu.stream()))
+        torch.cuda.synchronize()
+        outs.append(y)
+        stats.append(st)
+    assert torch.equal(outs[0], outs[1])
+    assert gu.rel(stats[1], stats[0]) <= 1e-6
+    if family == "fwd":
+        ref = F.conv2d(a, w, bias, stride=2, padding=1)
+    else:
+        ref = F.conv_transpose2d(a, w, bias, stride=2, padding=1, output_padding=1)
+    assert gu.rel(gu.nchw(outs[1]).cpu(), ref) <= gu.TOL[prec]
+
+
+@pytest.mark.parametrize("prec", gu.PRECISIONS)
 @pytest.mark.parametrize("batch", [1, 5])
 def test_thin_gather_fused_bnrelu_split_epilogue(batch, prec):
     """Conv2d(3,32) with the eval-mode epilogue: planes of relu(bn(conv1(x) + b)) bit-identical to the two-pass form."""
