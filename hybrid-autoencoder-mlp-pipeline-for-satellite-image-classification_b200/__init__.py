@@ -8,9 +8,9 @@ from .optim import Adam
 from .train import TrainStep
 from . import dp
 from .pipeline import extract_features, encode_predict
-from . import data, fit
+from . import data, fit, search
 from .data import DeviceDataset, DeviceLoader, TrainTransformAE, EvalTransform, augment_u8
 
 __all__ = ["Encoder", "Decoder", "SupervisedAutoencoder", "MLP", "Adam", "TrainStep", "dp", "extract_features",
-           "encode_predict", "default_backend", "default_precision", "data", "fit", "DeviceDataset", "DeviceLoader",
+           "encode_predict", "default_backend", "default_precision", "data", "fit", "search", "DeviceDataset", "DeviceLoader",
            "TrainTransformAE", "EvalTransform", "augment_u8"]

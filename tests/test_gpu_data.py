@@ -200,3 +200,30 @@ def test_full_pipeline_on_class_structured_data():
     x = ae_b200.EvalTransform()(te.images)
     _, _, am = ae_b200.encode_predict(res["model"].enc, res["clf"], x)
     assert abs(float((am == te.labels).float().mean()) - res["test_acc"]) <= 1e-6
+
+
+def test_grid_search_single_gpu_runs_the_reference_grid_order():
+    """NB:2629-2741 / NB:3447-3540 through search.fan_out on one device (the multi-rank exchange is covered on CPU with
+    gloo in tests/test_search_cpu.py): every configuration runs, the winner follows the strict-improvement rule."""
+    d = gu.dev()
+    tr = ae_b200.DeviceDataset(*_structured_u8(24, 11), device=d)
+    va = ae_b200.DeviceDataset(*_structured_u8(8, 12), device=d)
+    g = torch.Generator(device=d).manual_seed(3)
+    train = ae_b200.DeviceLoader(tr, 48, shuffle=True, transform=ae_b200.TrainTransformAE(generator=g, seed=1), generator=g)
+    val = ae_b200.DeviceLoader(va, 48)
+    torch.manual_seed(0)
+    res = ae_b200.search.grid_search_autoencoder([10.0, 35.0], [1e-3, 5e-3], train, val, num_epochs=2, patience=2)
+    assert len(res["results"]) == 4 and all(r is not None and r["epochs"] == 2 for r in res["results"])
+    losses = [r["best_val_loss"] for r in res["results"]]
+    assert res["best_index"] == losses.index(min(losses)) and res["best_config"] == ae_b200.search.ae_grid([10.0, 35.0], [1e-3, 5e-3])[res["best_index"]]
+    model = ae_b200.SupervisedAutoencoder(64, 10)
+    model.load_state_dict(res["best_state"])                           # the reference's checkpoint keys (NB:2735, NB:3431)
+    model = model.to(d).eval()
+    X, y = ae_b200.extract_features(val, model.enc)
+    Xt, yt = ae_b200.extract_features(ae_b200.DeviceLoader(tr, 48), model.enc)
+    mres = ae_b200.search.grid_search_mlp([1e-3, 1e-2], (Xt, yt), (X, y), num_epochs=3)
+    assert len(mres["results"]) == 2 and mres["best_index"] in (0, 1)
+    accs = [r["best_val_acc"] for r in mres["results"]]
+    assert mres["best"]["best_val_acc"] == max(accs)
+    clf = ae_b200.MLP(64, 10)
+    clf.load_state_dict(mres["best_state"])
