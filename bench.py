@@ -290,7 +290,6 @@ def run_ours(args):
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.summary()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -314,6 +313,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e = B * world * (1 if args.no_e2e else args.steps) / float(tt.item())
+    clocks = sampler.summary()      # sampled from the warm-up through both timed regions (device-resident and end-to-end)
     assert len(losses) == (1 if args.no_e2e else args.steps) and all(torch.isfinite(l).all() for l in losses)
 
     # ---- the dominant kernel on its own stream-ordered CUDA events (roofline), and encoder+MLP inference ----
