@@ -244,6 +244,13 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
 
   if (tid == 0) {
+    // the descriptors live in the kernel parameters: start fetching them while the CTA sets itself up
+    if (FAMILY == FAM_FPROP) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tma_prefetch_desc(&q.amap[i]);
+    } else {
+      tma_prefetch_desc(&q.amap[0]);
+    }
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     fence_barrier_init();
