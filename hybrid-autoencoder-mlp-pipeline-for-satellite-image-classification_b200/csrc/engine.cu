@@ -310,12 +310,12 @@ static int join_side(ae_engine* e, cudaStream_t st) {
   return 0;
 }
 
-// split-K of the two 4096-deep dense GEMMs: enough CTAs to fill the chip at small batches, fewer partials at large ones
+// split-K of the two 4096-deep dense GEMMs.  Fewer, deeper splits at large batches were tried (8 instead of 64 at batch
+// 4096: 89 + 7 us against 65 + 13 us for GEMM + reduce, profiles/r1_v8_every_kernel_full.txt): the CUDA-core kernel is
+// faster with many short K loops, so the split stays fixed.
 static int fc_split_for(const ae_engine* e, int batch) {
-  const int mtiles = (batch + 63) / 64;
-  int s = e->fc_split;
-  while (s > 1 && mtiles * s > 4 * 148) s >>= 1;
-  return s;
+  (void)batch;
+  return e->fc_split;
 }
 
 static int check_batch(const ae_engine* e, int batch) {
