@@ -98,3 +98,13 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("no oracle", ""), f
+
+
+def test_data_path_on_cpu_raises_instead_of_falling_back():
+    u8 = torch.zeros(4, 64, 64, 3, dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ae_b200.augment_u8(u8)
+    with pytest.raises(RuntimeError, match="uint8 images of shape"):
+        ae_b200.augment_u8(torch.zeros(4, 3, 64, 64))
+    # host-side pieces of the epoch statistics (NB:2686-2690) need no device
+    assert ae_b200.fit.weighted_mean(torch.tensor([[2.0, 0, 0], [4.0, 0, 0]]), [3, 1]) == pytest.approx(2.5)
