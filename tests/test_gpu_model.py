@@ -428,3 +428,20 @@ def test_frozen_encoder_and_feature_extraction():
         ref = tp.encoder_forward(st, torch.cat(xs), False)
     assert gu.rel(X, ref) <= 1e-4
     assert torch.equal(Y.cpu(), torch.cat(ys))
+
+
+def test_eval_encoder_walks_large_batches_in_chunks(monkeypatch):
+    """Inference over more images than AE_B200_EVAL_CHUNK (BASELINE configs[4]: batches up to 64k) walks the batch in
+    chunks of the engine's workspace size; images are independent in eval mode, so the latents must not depend on it."""
+    ae = ae_b200.SupervisedAutoencoder(64, backend=gu.BACKENDS[-1]).to(gu.dev())
+    st = gu.load_ae(ae, 13)
+    ae.enc.eval()
+    x = seeded.seeded_images(150, 77)
+    with torch.no_grad():
+        z_one = ae.enc(x.to(gu.dev())).clone()                     # one engine call (150 <= default chunk of 4096)
+        monkeypatch.setenv("AE_B200_EVAL_CHUNK", "64")
+        z_chunked = ae.enc(x.to(gu.dev()))                         # 64 + 64 + 22
+        ref = tp.encoder_forward(st, x, False)
+    torch.cuda.synchronize()
+    assert gu.rel(z_chunked, z_one) <= 1e-6
+    assert gu.rel(z_chunked, ref) <= 1e-4
