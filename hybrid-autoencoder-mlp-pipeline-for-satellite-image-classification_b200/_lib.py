@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libae_b200.so")
+LIB_PATH = os.environ.get("AE_B200_LIB") or os.path.join(_HERE, "libae_b200.so")   # AE_B200_LIB: developer builds only
 
 PREC_FP32, PREC_BF16 = 0, 1
 BACKEND_TC, BACKEND_SIMT = 0, 1

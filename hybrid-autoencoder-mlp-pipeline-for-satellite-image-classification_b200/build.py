@@ -15,12 +15,15 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libae_b200.so")
+# AE_B200_BUILD_VARIANT=trace: developer build with per-CTA phase timestamps in the row GEMM (-DAE_TRACE), written to
+# libae_b200_trace.so; the product library never contains that code
+VARIANT = os.environ.get("AE_B200_BUILD_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libae_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 SOURCES = ["api.cu", "simt_gemm.cu", "thin.cu", "thin_tc.cu", "elementwise.cu", "head.cu", "mlp.cu", "tma_gemm.cu", "engine.cu", "dp.cu", "augment.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + (["-DAE_TRACE"] if VARIANT == "trace" else [])
 
 
 def _deps_mtime():

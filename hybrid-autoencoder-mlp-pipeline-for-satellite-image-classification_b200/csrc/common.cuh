@@ -88,19 +88,6 @@ struct BnJob {
   float* dzero;      // BWD: C floats set to zero by the job -- the gradient of the bias that feeds this BatchNorm (or NULL)
 };
 
-// Work a row-GEMM launch can append to itself once EVERY CTA of the grid has finished (grid barrier): the BatchNorm
-// coefficient job of the tensor it just wrote and that tensor's conversion into the consumer's split-bf16 operand planes
-// -- what k_split_operand does as a launch of its own.  Experimental (AE_B200_FUSED_TAIL=1), see DESIGN.md 9a-1.
-struct SplitTail {
-  int enabled;
-  BnJob job;                 // BN_JOB_FINALIZE (forward) or BN_JOB_BWD (backward) of the written tensor's BatchNorm
-  Operand op;                // BNRELU(y, bnc) / BNBWD(dz, y, bnc); op.src is the tensor this launch writes
-  void* planes;              // destination planes, or NULL: coefficient job only
-  long long n8;              // elements / 8
-  long long plane_elems;
-  unsigned int* sync;        // two counters (arrive, depart), zero between launches
-};
-
 struct Geom {
   int B, Hs, Ws, Cb, Cs;
   int lHs, lWs;      // log2
@@ -247,8 +234,7 @@ size_t tma_packed_bytes(int Cs, int Cb, int nsplit);
 int tma_pack_conv(const float* w, int Cs, int Cb, int nsplit, void* fwd, void* dgrad, cudaStream_t st);
 int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit, const BnJob* job, cudaStream_t st);
 int run_bn_job(const BnJob& job, cudaStream_t st);   // the same job as stand-alone launches
-int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st,    // p.A: AE_OP_SPLIT_BF16
-                const SplitTail* tail = nullptr);
+int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);   // p.A: AE_OP_SPLIT_BF16
 bool tma_rowgemm_supported(const RowGemm& p);
 bool tma_wgrad_supported(const Geom& g);
 int tma_wgrad_slices(const Geom& g);

@@ -128,13 +128,6 @@ struct ae_engine {
   ae_dp_comm_t* step_comm = nullptr;
   bool defer_conv1_wgrad = false;     // the captured step runs conv1's weight gradient beside Adam + re-pack of everything else
   bool stats_cleared = false;         // the fused step zeroed every statistic accumulator in one memset: the parts skip theirs
-  // Experimental (AE_B200_FUSED_TAIL=1; written but not yet run on hardware): the row GEMM that writes a
-  // tensor also runs that tensor's BatchNorm coefficient job and converts it into the consumer's operand planes behind a
-  // grid barrier, instead of a k_split_operand / k_bn_* launch in front of the consumer.
-  bool fused_tail = false;
-  void* dy_pl2 = nullptr;             // second gradient-plane buffer: a tail writes the next layer's planes while the
-                                      // current layer's weight gradient still reads the current ones
-  unsigned int* tail_sync = nullptr;  // grid-barrier counters (self-resetting)
   // pointers remembered between forward and backward
   const float* last_x = nullptr;
   const float* last_z_dec = nullptr;
@@ -226,7 +219,6 @@ static size_t carve(ae_engine* e, char* base) {
     for (int i = 0; i < 2; ++i) e->ad_pl[i] = take(tsz[i] * pb);
     e->h_pl = take(B * 4096 * pb);
     e->dy_pl = take(tsz[2] * pb);
-    if (e->fused_tail) e->dy_pl2 = take(tsz[2] * pb);
   }
   e->z = (float*)take(B * L * 4);
   e->dz_dec = (float*)take(B * L * 4);
@@ -291,8 +283,7 @@ static size_t carve(ae_engine* e, char* base) {
   e->head_partial = (float*)take(head_fused_workspace_floats((int)B, L, NC) * 4);
   e->partial_side_bytes = (size_t)colgemm_default_split((int)B, 4096, L) * 4096 * L * 4;
   e->partial_side = (float*)take(e->partial_side_bytes);
-  e->head_counter = (unsigned int*)take(256);      // [0..31]: head; [32..33]: grid-barrier counters of the fused tail
-  e->tail_sync = e->head_counter + 32;
+  e->head_counter = (unsigned int*)take(256);
   return off + 256;
 }
 
@@ -360,21 +351,12 @@ static BnJob bn_bwd_job(const Part& P, int l, int batch, float* dzero) {
   return j;
 }
 
-// Fused tail of a row GEMM (see ae_engine::fused_tail): `op` describes the tensor the launch writes together with the
-// transform its consumer wants (NULL planes: coefficient job only).
-static SplitTail make_tail(const ae_engine* e, const BnJob& job, const Operand& op, void* planes, int64_t count) {
-  SplitTail t;
-  memset(&t, 0, sizeof(t));
-  t.enabled = 1; t.job = job; t.op = op; t.planes = planes; t.n8 = count / 8; t.plane_elems = count; t.sync = e->tail_sync;
-  return t;
-}
-
 // Row GEMM of a mid layer.  `a` is the fp32 operand description (transform included); on the tcgen05 path its
 // split-bf16 planes are `planes`: produced here when `split_now`, else already current (written earlier this step).
 // `job`: the BatchNorm coefficient job of the operand's layer; it runs inside the split kernel (tcgen05 path) or as its
 // own launch (CUDA-core path).
 static int run_rowgemm(ae_engine* e, RowGemm& r, const Operand& a, void* planes, bool split_now, int64_t a_count,
-                       const void* pk, const BnJob* job, cudaStream_t st, const SplitTail* tail = nullptr) {
+                       const void* pk, const BnJob* job, cudaStream_t st) {
   if (e->simt) {
     if (job) AE_TRY(run_bn_job(*job, st));
     r.A = a;
@@ -383,7 +365,7 @@ static int run_rowgemm(ae_engine* e, RowGemm& r, const Operand& a, void* planes,
   if (split_now) AE_TRY(tma_split_operand(a, a_count, planes, e->nsplit, job, st));
   else if (job) AE_TRY(run_bn_job(*job, st));
   r.A = split_operand(planes, a.C);
-  return tma_rowgemm(r, pk, e->nsplit, st, tail);
+  return tma_rowgemm(r, pk, e->nsplit, st);
 }
 
 // Weight gradient of a mid layer: big / small are the fp32 operand descriptions; on the tcgen05 path the planes
@@ -425,8 +407,6 @@ int ae_engine_create(const ae_engine_config_t* cfg, ae_engine_t** out) {
   e->L = cfg->latent_dim; e->NC = cfg->num_classes; e->Bmax = cfg->max_batch;
   e->simt = cfg->backend == AE_BACKEND_SIMT;
   e->nsplit = cfg->precision == AE_PREC_FP32 ? 2 : 1;
-  const char* ft = getenv("AE_B200_FUSED_TAIL");
-  e->fused_tail = !e->simt && ft != nullptr && atoi(ft) == 1;
   build_layouts(e);
   e->ws_need = carve(e, nullptr);
   *out = e;
@@ -592,19 +572,10 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
       continue;
     }
     const BnJob job = bn_fwd_job(P, i, batch, training);      // BatchNorm of this layer's input, finalised in the split
-    if (e->fused_tail && training) {
-      // the previous layer's launch already produced this layer's planes (i >= 1); this launch produces the next layer's
-      const BnJob njob = bn_fwd_job(P, i + 1, batch, 1);
-      const SplitTail tail = make_tail(e, njob, bnrelu_operand(e->y[i + 1], bout.bnc, bout.C), i < 2 ? e->ae_pl[i + 1] : nullptr,
-                                       (int64_t)batch * bout.count_per_image * bout.C);
-      AE_TRY(run_rowgemm(e, r, bnrelu_operand(e->y[i], bin.bnc, bin.C), e->ae_pl[i], i == 0,
-                         (int64_t)batch * bin.count_per_image * bin.C, m.pk_fwd, i == 0 ? &job : nullptr, st, &tail));
-      continue;
-    }
     AE_TRY(run_rowgemm(e, r, bnrelu_operand(e->y[i], bin.bnc, bin.C), e->ae_pl[i], true,
                        (int64_t)batch * bin.count_per_image * bin.C, m.pk_fwd, &job, st));
   }
-  if (!fused_eval && !(e->fused_tail && training)) AE_TRY(run_bn_job(bn_fwd_job(P, 3, batch, training), st));
+  if (!fused_eval) AE_TRY(run_bn_job(bn_fwd_job(P, 3, batch, training), st));
   {  // Flatten + Linear(4096, L): split-K partials, fixed-order reduce (+bias)
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = e->L; r.K = 4096;
@@ -661,12 +632,8 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     const Operand a_big = bnrelu_operand(e->y[i], bin.bnc, bin.C);                          // planes: ae_pl[i] (forward)
     const Operand dy_small = bnbwd_operand(e->dzy[i + 1], e->y[i + 1], bout.bnc, bout.C);   // planes: dy_pl (now)
     const BnJob job = bn_bwd_job(P, i + 1, batch, P.G(m.b));  // backward coefficients of the output BatchNorm (+ zero bias gradient)
-    // fused tail: the planes of iteration i were written by iteration i+1's data-gradient launch into the buffer that
-    // alternates with the one its own weight gradient was reading
-    void* dyp = e->fused_tail && ((2 - i) & 1) ? e->dy_pl2 : e->dy_pl;
-    void* dyn = dyp == e->dy_pl ? e->dy_pl2 : e->dy_pl;
-    const bool have_planes = e->fused_tail && i < 2;
-    if (!e->simt) { if (!have_planes) AE_TRY(tma_split_operand(dy_small, (int64_t)Mrows * m.g.Cs, dyp, e->nsplit, &job, st)); }
+    void* dyp = e->dy_pl;
+    if (!e->simt) AE_TRY(tma_split_operand(dy_small, (int64_t)Mrows * m.g.Cs, dyp, e->nsplit, &job, st));
     else AE_TRY(run_bn_job(job, st));
     // the weight gradient runs beside the data gradient (both only read the dy planes)
     if (!e->simt) AE_TRY(fork_side(e, st));
@@ -676,19 +643,10 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     r.Bp = (const float*)m.pk_dgrad;
     r.epi = relubwd_epilogue(e->y[i], bin.bnc, bin.stats_b, bin.C);
     r.out = e->dzy[i]; r.splitK = 1;
-    if (e->fused_tail) {
-      // this launch writes dzy[i] and the statistics of BatchNorm i: its tail runs that layer's backward job and, for
-      // i >= 1, converts dy = bn_bwd(dzy[i], y[i]) into the next iteration's planes
-      const BnJob njob = bn_bwd_job(P, i, batch, i >= 1 ? P.G(e->enc_mid[i - 1].b) : P.G(1));
-      const SplitTail tail = make_tail(e, njob, bnbwd_operand(e->dzy[i], e->y[i], bin.bnc, bin.C), i >= 1 ? dyn : nullptr,
-                                       (int64_t)batch * bin.count_per_image * bin.C);
-      AE_TRY(run_rowgemm(e, r, dy_small, dyp, false, 0, m.pk_dgrad, nullptr, st, &tail));
-    } else {
-      AE_TRY(run_rowgemm(e, r, dy_small, dyp, false, 0, m.pk_dgrad, nullptr, st));
-    }
+    AE_TRY(run_rowgemm(e, r, dy_small, dyp, false, 0, m.pk_dgrad, nullptr, st));
     if (!e->simt) AE_TRY(join_side(e, st));
   }
-  if (!e->fused_tail) AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch, P.G(1)), st));
+  AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch, P.G(1)), st));
   if (!e->defer_conv1_wgrad) AE_TRY(conv1_wgrad(e, batch, st));
   return 0;
 }
@@ -740,19 +698,10 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
     }
     BnJob job{};
     if (i > 0) job = bn_fwd_job(P, i - 1, batch, training);
-    if (e->fused_tail && training) {
-      // this launch writes t[i] and the statistics of BatchNorm i: its tail finalises them and (i < 2) writes the planes
-      // the next transposed convolution reads; its own operand planes come from the dense layer (i = 0) or the previous tail
-      const BnJob njob = bn_fwd_job(P, i, batch, 1);
-      const SplitTail tail = make_tail(e, njob, bnrelu_operand(e->t[i], bout.bnc, bout.C), i < 2 ? e->ad_pl[i] : nullptr,
-                                       (int64_t)batch * bout.count_per_image * bout.C);
-      AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], false, 0, m.pk_dgrad, nullptr, st, &tail));
-      continue;
-    }
     AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], i > 0 || e->simt, (int64_t)r.M * m.g.Cs, m.pk_dgrad,
                        i > 0 ? &job : nullptr, st));
   }
-  if (!fused_eval && !(e->fused_tail && training)) AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
+  if (!fused_eval) AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
   float* xo = x_hat ? x_hat : e->xhat;
   // (thin_tc_scatter_sigmoid_fwd: same speed as the fp32 CUDA-core kernel, which is the more exact one)
   AE_TRY(thin_scatter_sigmoid_fwd(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), P.P(14), P.P(15), xo, x_target, e->sse, batch, st));
@@ -798,10 +747,8 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     const Operand dy_big = bnbwd_operand(e->dzt[i], e->t[i], bout.bnc, bout.C);     // planes: dy_pl (now)
     Geom g = m.g; g.B = batch;
     const BnJob job = bn_bwd_job(P, i, batch, P.G(m.b));
-    void* dyp = e->fused_tail && ((2 - i) & 1) ? e->dy_pl2 : e->dy_pl;       // see ae_encoder_backward
-    void* dyn = dyp == e->dy_pl ? e->dy_pl2 : e->dy_pl;
-    const bool have_planes = e->fused_tail && i < 2;
-    if (!e->simt) { if (!have_planes) AE_TRY(tma_split_operand(dy_big, (int64_t)Mrows * 4 * m.g.Cb, dyp, e->nsplit, &job, st)); }
+    void* dyp = e->dy_pl;
+    if (!e->simt) AE_TRY(tma_split_operand(dy_big, (int64_t)Mrows * 4 * m.g.Cb, dyp, e->nsplit, &job, st));
     else AE_TRY(run_bn_job(job, st));
     if (!e->simt) AE_TRY(fork_side(e, st));
     AE_TRY(run_conv_wgrad(e, g, dy_big, small, dyp, i == 0 ? e->h_pl : e->ad_pl[i - 1], P.G(m.w), e->simt ? st : e->side));
@@ -811,16 +758,7 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
     if (i == 0) { r.epi = store_epilogue(); r.epi.C = m.g.Cs; r.out = e->dh; }
     else { BN& bin = P.bn[i - 1]; r.epi = relubwd_epilogue(e->t[i - 1], bin.bnc, bin.stats_b, bin.C); r.out = e->dzt[i - 1]; }
     r.splitK = 1;
-    if (e->fused_tail && i >= 1) {
-      // this launch writes dzt[i-1] and the statistics of BatchNorm i-1: backward job + the next iteration's planes
-      BN& bin = P.bn[i - 1];
-      const BnJob njob = bn_bwd_job(P, i - 1, batch, P.G(e->dec_mid[i - 1].b));
-      const SplitTail tail = make_tail(e, njob, bnbwd_operand(e->dzt[i - 1], e->t[i - 1], bin.bnc, bin.C), dyn,
-                                       (int64_t)batch * bin.count_per_image * bin.C);
-      AE_TRY(run_rowgemm(e, r, dy_big, dyp, false, 0, m.pk_fwd, nullptr, st, &tail));
-    } else {
-      AE_TRY(run_rowgemm(e, r, dy_big, dyp, false, 0, m.pk_fwd, nullptr, st));
-    }
+    AE_TRY(run_rowgemm(e, r, dy_big, dyp, false, 0, m.pk_fwd, nullptr, st));
     if (!e->simt) AE_TRY(join_side(e, st));
   }
   {  // decoder_input backward

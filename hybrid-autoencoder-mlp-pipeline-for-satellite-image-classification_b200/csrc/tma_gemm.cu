@@ -195,6 +195,20 @@ int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit
 // ---------------------------------------------------------------------------------------------
 static constexpr int RG_THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2..5: epilogue
 
+// Developer build only (python build.py with AE_B200_BUILD_VARIANT=trace): per-CTA phase timestamps of the row GEMM, read
+// back by scripts/trace_rowgemm.py.  The product library is compiled without AE_TRACE and contains none of this.
+#ifdef AE_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define AE_TR(slot) do { if (g_trace) g_trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+#else
+#define AE_TR(slot) do { } while (0)
+#endif
+
 struct alignas(64) TmaRow {
   CUtensorMap amap[4];      // FPROP: parity lattices (py*2+px) of the big image; DGRAD: [0] = small image
   const uint8_t* wtiles;    // packed weight tiles
@@ -205,131 +219,12 @@ struct alignas(64) TmaRow {
   int cpt;                  // K chunks per tap (C / KC)
   int wchunks;              // K chunks per n-tile in the weight pack (all taps / all phases)
   int bx, by, bn;           // pixel box of one 128-row tile
-  SplitTail tail;           // TAIL instantiations only
 };
-
-// ---- fused tail (experimental): grid barrier + what k_split_operand does, inside the producing launch ----------------
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// One-shot barrier over all CTAs of a grid whose CTAs are all co-resident (the launcher sizes the grid by occupancy).
-// Bounded: a protocol error traps instead of hanging the GPU.  The last CTA out resets both counters for the next launch.
-__device__ __forceinline__ void grid_barrier_once(unsigned int* sync, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(sync, 1u);
-    unsigned int spins = 0;
-    while (ld_acquire_u32(sync) < nblocks) {
-      __nanosleep(40);
-      if (++spins > (1u << 25)) {
-        printf("ae_b200: grid barrier timed out (block %d of %d)\n", (int)blockIdx.x, (int)nblocks);
-        __trap();
-      }
-    }
-    __threadfence();
-    if (atomicAdd(sync + 1, 1u) == nblocks - 1) { sync[1] = 0u; sync[0] = 0u; __threadfence(); }
-  }
-  __syncthreads();
-}
-
-// coefficients of the tail's BatchNorm job into sc (same arithmetic as the prologue of k_split_operand; the statistics
-// were accumulated by other SMs during this launch, so they are read past L1)
-__device__ __forceinline__ void tail_coefficients(const SplitTail& t, float (*sc)[256], bool publisher, int tid, int nthreads) {
-  const BnJob& job = t.job;
-  const int C = job.C;
-  for (int c = tid; c < C; c += nthreads) {
-    if (job.kind == BN_JOB_FINALIZE) {
-      const double mean = __ldcg(job.stats + c) / job.count;
-      double var = __ldcg(job.stats + C + c) / job.count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-      const float scale = job.gamma[c] * rstd;
-      const float shift = job.beta[c] - (float)mean * scale;
-      sc[0][c] = scale; sc[1][c] = shift;
-      if (publisher) {
-        if (c == 0 && job.nbt) *job.nbt += 1;
-        if (job.rmean) {
-          const double unb = job.count > 1.0 ? var * job.count / (job.count - 1.0) : var;
-          job.rmean[c] = (float)(0.9 * (double)job.rmean[c] + 0.1 * mean);
-          job.rvar[c] = (float)(0.9 * (double)job.rvar[c] + 0.1 * unb);
-        }
-        job.bnc[AE_BNC_SCALE * C + c] = scale; job.bnc[AE_BNC_SHIFT * C + c] = shift;
-        job.bnc[AE_BNC_MEAN * C + c] = (float)mean; job.bnc[AE_BNC_RSTD * C + c] = rstd;
-      }
-    } else {                                              // BN_JOB_BWD
-      const double s1 = __ldcg(job.stats + c), s2 = __ldcg(job.stats + C + c);
-      const double rstd = (double)job.bnc[AE_BNC_RSTD * C + c];
-      const double a = (double)job.gamma[c] * rstd;
-      const float fa = (float)a, fb = (float)(-a * rstd * s2 / job.count), fk = (float)(-a * s1 / job.count);
-      sc[0][c] = fa; sc[1][c] = fb; sc[2][c] = fk; sc[3][c] = job.bnc[AE_BNC_MEAN * C + c];
-      if (publisher) {
-        job.bnc[AE_BNC_A * C + c] = fa; job.bnc[AE_BNC_B * C + c] = fb; job.bnc[AE_BNC_C * C + c] = fk;
-        if (job.dgamma) job.dgamma[c] = (float)s2;
-        if (job.dbeta) job.dbeta[c] = (float)s1;
-        if (job.dzero) job.dzero[c] = 0.f;
-      }
-    }
-  }
-}
-
-// the written tensor -> operand transform -> split-bf16 planes; four independent 32-byte loads in flight per thread
-template <int NSPLIT>
-__device__ __forceinline__ void tail_convert(const SplitTail& t, const float (*sc)[256], int tid, int nthreads) {
-  const Operand& op = t.op;
-  const int C = op.C;
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(t.planes);
-  const long long stride = (long long)gridDim.x * nthreads;
-  for (long long i0 = (long long)blockIdx.x * nthreads + tid; i0 < t.n8; i0 += 4 * stride) {
-    float4 a0[4], a1[4], y0[4], y1[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < t.n8) {
-        const float4* src = reinterpret_cast<const float4*>(op.src + (size_t)i * 8);   // written during this launch: past L1
-        a0[u] = __ldcg(src); a1[u] = __ldcg(src + 1);
-        if (op.mode == AE_OP_BNBWD) {
-          const float4* s2 = reinterpret_cast<const float4*>(op.src2 + (size_t)i * 8);
-          y0[u] = __ldg(s2); y1[u] = __ldg(s2 + 1);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long long i = i0 + u * stride;
-      if (i >= t.n8) break;
-      const size_t off = (size_t)i * 8;
-      const int c = (int)(off % (size_t)C);
-      float v[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
-      if (op.mode == AE_OP_BNRELU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[0][c + j], sc[1][c + j]), 0.f);
-      } else {                                            // AE_OP_BNBWD, same order of operations as k_split_operand
-        const float y[8] = {y0[u].x, y0[u].y, y0[u].z, y0[u].w, y1[u].x, y1[u].y, y1[u].z, y1[u].w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(sc[0][c + j], v[j], fmaf(sc[1][c + j], y[j] - sc[3][c + j], sc[2][c + j]));
-      }
-      uint4 hi;
-      hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]); hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(dst + off) = hi;
-      if (NSPLIT == 2) {
-        float r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
-        uint4 lo;
-        lo.x = pack_bf16x2(r[0], r[1]); lo.y = pack_bf16x2(r[2], r[3]); lo.z = pack_bf16x2(r[4], r[5]); lo.w = pack_bf16x2(r[6], r[7]);
-        *reinterpret_cast<uint4*>(dst + t.plane_elems + off) = lo;
-      }
-    }
-  }
-}
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A tile is (phase, m-tile, n-tile) with
 // the n-tile fastest.  The accumulator is double-buffered in tensor memory, so the epilogue of tile i overlaps the
 // TMA loads and MMAs of tile i+1, and barrier / TMEM set-up is paid once per CTA.
-template <int FAMILY, int NT, int KC, int NSPLIT, int STAGES, bool TAIL = false>
+template <int FAMILY, int NT, int KC, int NSPLIT, int STAGES>
 __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constant__ TmaRow q) {
   constexpr int ROWB = KC * 2;                                // bytes per shared-memory row
   constexpr uint32_t A_PLANE = TILE_M * ROWB;
@@ -352,6 +247,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
 
   const Geom g = q.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) AE_TR(0);
   const int tiles_m = (q.M + TILE_M - 1) / TILE_M, tiles_n = q.N / NT;
   const int tiles_mn = tiles_m * tiles_n;
   const int num_tiles = tiles_mn * (FAMILY == FAM_DGRAD ? 4 : 1);
@@ -395,6 +291,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (tid == 0) AE_TR(1);
 
   // tile -> (phase, ntile, m0, number of K chunks, first chunk inside the weight pack)
   auto decode = [&](int tile, int& phase, int& ntile, int& m0, int& nkc, int& kc_off) {
@@ -452,8 +349,10 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
                 bulk_copy_g2s(a_dst + A_BYTES + pl * B_PLANE + sub * PK_PLANE,
                               wsrc + ((size_t)sub * q.wchunks + it) * (NSPLIT * PK_PLANE) + pl * PK_PLANE, PK_PLANE, full_bar(s));
           }
+          if (gc == 0) AE_TR(2);
         }
       }
+      AE_TR(3);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -471,6 +370,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
           const uint32_t s = gc % STAGES, round = gc / STAGES;
           mbar_wait(full_bar(s), round & 1);
           tc_fence_after();
+          if (gc == 0) AE_TR(4);
           const uint32_t a0 = smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint32_t b0 = a0 + A_BYTES;
 #pragma unroll
@@ -488,6 +388,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
         }
         umma_commit(tfull_bar(ab));
       }
+      AE_TR(5);
     }
     __syncwarp();
   } else {
@@ -516,11 +417,13 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
       }
       mbar_wait(tfull_bar(ab), (ti >> 1) & 1);
       tc_fence_after();
+      if (et == 0) { if (ti == 0) AE_TR(6); AE_TR(7); }
 #pragma unroll 1
       for (int col0 = 0; col0 < NT; col0 += 32) {
         const int n = ntile * NT + col0;                 // global output channel
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + ab * NT + (uint32_t)col0, v);
+        if (et == 0 && col0 == 0) AE_TR(11);
         if (col0 + 32 >= NT) {                           // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -566,14 +469,17 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
             for (int j8 = 0; j8 < 4; ++j8) st_global_v8(q.out + orow + n + j8 * 8, v, j8);
           }
         }
+        if (et == 0 && col0 == 0) AE_TR(12);
         if (do_stats) {
           const float a = warp_colsum32_tc(v, lane);
           const float b = warp_colsum32_tc(s2, lane);
           atomicAdd(&sStat[0][n + lane], a);
           atomicAdd(&sStat[1][n + lane], b);
         }
+        if (et == 0 && col0 == 0) AE_TR(13);
       }
     }
+    if (et == 0) AE_TR(8);
     if (do_stats) {                                         // one flush per CTA: fp64 atomics, one per channel
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = et; c < q.N; c += 128) {
@@ -585,6 +491,7 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
         }
       }
     }
+    if (et == 0) AE_TR(9);
   }
   tc_fence_before();
   __syncthreads();
@@ -592,15 +499,14 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
-  if constexpr (TAIL) {
-    // every CTA has stored its tiles and flushed its statistics: coefficients, then the consumer's operand planes
-    __shared__ float tsc[4][256];
-    grid_barrier_once(q.tail.sync, gridDim.x);
-    tail_coefficients(q.tail, tsc, blockIdx.x == 0, tid, RG_THREADS);
-    __syncthreads();
-    if (q.tail.planes) tail_convert<NSPLIT>(q.tail, tsc, tid, RG_THREADS);
-  }
+  if (tid == 0) AE_TR(10);
 }
+
+#ifdef AE_TRACE
+extern "C" int ae_debug_set_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // weight packing: w [Cs][Cb][3][3] fp32 -> swizzled bf16 (hi[, lo]) tiles for both row-GEMM orientations.
@@ -671,24 +577,6 @@ template <int FAMILY, int NT, int KC, int NSPLIT, int STAGES>
 static int launch_row(const TmaRow& q, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * NSPLIT * (TILE_M * KC * 2 + NT * KC * 2) + 1024;
   const int tiles = (int)(grid.x * grid.y * grid.z);
-  if (q.tail.enabled) {
-    // the fused tail waits at a grid barrier: the grid must be exactly what the device keeps resident at once
-    static bool attr_tail = false;
-    if (!attr_tail) {
-      AE_CUDA(cudaFuncSetAttribute(k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_tail = true;
-    }
-    int dev = 0, sms = 0, occ = 0;
-    AE_CUDA(cudaGetDevice(&dev));
-    AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES, true>, RG_THREADS, smem));
-    AE_CHECK(occ >= 1, "tma_rowgemm: the fused-tail kernel does not fit on an SM");
-    if (occ > 2) occ = 2;
-    const int ctas = tiles < occ * sms ? tiles : occ * sms;
-    k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES, true><<<ctas, RG_THREADS, smem, st>>>(q);
-    AE_LAUNCH_CHECK();
-    return 0;
-  }
   static bool attr_done = false;
   if (!attr_done) {
     AE_CUDA(cudaFuncSetAttribute(k_tma_rowgemm<FAMILY, NT, KC, NSPLIT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -702,7 +590,7 @@ static int launch_row(const TmaRow& q, dim3 grid, cudaStream_t st) {
 }
 
 // p.A.src must point to the split-bf16 planes of the A image (AE_OP_SPLIT_BF16)
-int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st, const SplitTail* tail) {
+int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st) {
   AE_CHECK(tma_rowgemm_supported(p), "tma_rowgemm: unsupported shape");
   AE_CHECK(p.A.mode == AE_OP_SPLIT_BF16, "tma_rowgemm: the A operand must be split-bf16 planes (ae_split_operand)");
   AE_CHECK(((uintptr_t)packed & 15) == 0, "tma_rowgemm: packed weights must be 16-byte aligned");
@@ -710,14 +598,6 @@ int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t s
   memset(&q, 0, sizeof(q));
   q.wtiles = (const uint8_t*)packed;
   q.g = p.g; q.epi = p.epi; q.out = p.out; q.M = p.M; q.N = p.N;
-  if (tail && tail->enabled) {
-    AE_CHECK(tail->sync != nullptr && (tail->job.kind == BN_JOB_FINALIZE || tail->job.kind == BN_JOB_BWD) && tail->job.C <= 256,
-             "tma_rowgemm: malformed fused tail");
-    AE_CHECK(tail->planes == nullptr || ((tail->op.mode == AE_OP_BNRELU || tail->op.mode == AE_OP_BNBWD) && tail->op.C == tail->job.C &&
-                                         tail->op.C % 8 == 0 && ((uintptr_t)tail->planes & 15) == 0),
-             "tma_rowgemm: fused tail operand does not match its BatchNorm job");
-    q.tail = *tail;
-  }
   const Geom& g = p.g;
   pixel_box(g.Hs, g.Ws, TILE_M, &q.bx, &q.by, &q.bn);
   // 64-wide n-tiles keep the most CTAs busy at training batch sizes; with thousands of m-tiles (inference) a 128-wide tile
