@@ -128,22 +128,67 @@ def synthetic_batches(n_batches, batch, seed, pin):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference loop body on the host cores
+# CPU baseline / reference arm.  kind "reference": the reference's OWN classes (the notebook's cells, executed by
+# oracle/load_reference.py from /root/reference or from the git-ignored copy under baseline/_ref) driven by the literal loop
+# body NB:2676-2684 with torch.optim.Adam (NB:2654).  kind "port": oracle/torch_port.py's functional restatement with the
+# same torch.optim.Adam, when no notebook can be found.
 # --------------------------------------------------------------------------------------------------
-def cpu_train_steps(batch, steps, warmup):
+def reference_step_fn(device):
+    """Returns (step(x, y) -> loss tensor, kind, description): one iteration of NB:2676-2684 on `device` in stock PyTorch."""
+    import torch.nn as nn
+    try:
+        from oracle import load_reference
+        if load_reference.reference_available():
+            cls = load_reference.load_reference_classes()
+            torch.manual_seed(0)
+            model = cls["SupervisedAutoencoder"](64, 10).to(device)
+            model.train()
+            mse, ce = nn.MSELoss(), nn.CrossEntropyLoss()
+            opt = torch.optim.Adam(model.parameters(), lr=LR)
+
+            def step(x, y):
+                opt.zero_grad()
+                x_hat, logits, _ = model(x)
+                loss = ALPHA * mse(x_hat, x) + ce(logits, y)
+                loss.backward()
+                opt.step()
+                return loss
+            return step, "reference", "the notebook's SupervisedAutoencoder + loop body NB:2676-2684, torch.optim.Adam"
+    except Exception as ex:                                   # fall through to the port
+        print(f"bench: reference classes unavailable ({ex}); timing the oracle port", file=sys.stderr)
     from oracle import seeded, torch_port as tp
-    torch.manual_seed(0)
     st = seeded.seeded_state(seeded.ae_state_shapes(64, 10), 0)
+    st = {k: v.to(device) for k, v in st.items()}
+    keys = tp.param_keys(st)
+    leaves = {k: st[k].detach().clone().requires_grad_(True) for k in keys}
+    opt = torch.optim.Adam([leaves[k] for k in keys], lr=LR)
+
+    def step(x, y):
+        opt.zero_grad()
+        work = dict(st)
+        work.update(leaves)
+        nb = {}
+        x_hat, logits, _ = tp.ae_forward(work, x, True, nb)
+        loss, _, _ = tp.ae_loss(x_hat, logits, x, y, ALPHA)
+        loss.backward()
+        opt.step()
+        st.update(nb)
+        return loss
+    return step, "port", "oracle/torch_port.py forward + torch autograd + torch.optim.Adam"
+
+
+def cpu_train_steps(batch, steps, warmup):
+    torch.manual_seed(0)
+    step, kind, what = reference_step_fn(torch.device("cpu"))
     x = torch.rand(batch, 3, 64, 64)
     y = torch.randint(0, 10, (batch,))
-    opt = {}
     for _ in range(warmup):
-        tp.ae_train_step(st, opt, x, y, ALPHA, LR)
+        step(x, y)
     t0 = time.perf_counter()
     for _ in range(steps):
-        tp.ae_train_step(st, opt, x, y, ALPHA, LR)
+        float(step(x, y))                                     # NB:2687: loss.item() every step
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    return batch * steps / dt, dt / steps, kind, what
 
 
 def run_reference(args):
@@ -153,18 +198,87 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     steps = max(1, min(args.steps, 40))
-    ips, per = cpu_train_steps(args.batch, steps, max(1, min(args.warmup, 3)))
+    ips, per, kind, what = cpu_train_steps(args.batch, steps, max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": max(1, min(args.warmup, 3)), "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": "supervised AE train step (alpha*MSE + CE, Adam), batch 256, 3x64x64, latent 64",
                    "batch_per_step": args.batch},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{steps} train steps of batch {args.batch} (oracle/torch_port.py, torch CPU fp32)"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": f"{steps} train steps of batch {args.batch} ({what}; torch CPU fp32)"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# Stock PyTorch on the same B200 (SURVEY 8d "the real bar"): the reference modules, eager, default torch settings, the
+# literal loop body with a device-resident batch; and the drop-in loop of INTEGRATION.md section 1 (the same Python loop
+# with ae_b200's modules and optimizer: three autograd Functions + the fused flat Adam, no whole-step graph).
+# --------------------------------------------------------------------------------------------------
+def _time_loop(step, xs, ys, steps, warmup):
+    for i in range(warmup):
+        step(xs[i % len(xs)], ys[i % len(ys)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for i in range(steps):
+        last = step(xs[i % len(xs)], ys[i % len(ys)])
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / steps, float(last)
+
+
+def torch_gpu_baseline(dev, B, xs, ys, steps=50, warmup=10):
+    step, kind, what = reference_step_fn(dev)
+    t, loss = _time_loop(step, xs, ys, steps, warmup)
+    return {"value": B / t, "unit": "images/s", "ms_per_step": t * 1e3, "kind": kind, "what": what + "; eager, CUDA, device-resident batches",
+            "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32), "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
+            "steps": steps, "final_loss": loss}
+
+
+def dropin_loop(dev, B, xs, ys, precision, backend, steps=50, warmup=10):
+    import torch.nn as nn
+    import ae_b200
+    torch.manual_seed(0)
+    model = ae_b200.SupervisedAutoencoder(64, 10, precision=precision, backend=backend).to(dev).train()
+    model.engine().prepare(dev, B)
+    opt = ae_b200.Adam(model.parameters(), lr=LR)
+    mse, ce = nn.MSELoss(), nn.CrossEntropyLoss()
+
+    def step(x, y):                                           # INTEGRATION.md section 1 = NB:2676-2684 verbatim
+        opt.zero_grad()
+        x_hat, logits, _ = model(x)
+        loss = ALPHA * mse(x_hat, x) + ce(logits, y)
+        loss.backward()
+        opt.step()
+        return loss
+    t, loss = _time_loop(step, xs, ys, steps, warmup)
+    return {"value": B / t, "unit": "images/s", "ms_per_step": t * 1e3, "steps": steps, "final_loss": loss,
+            "what": "model(imgs); alpha*mse + ce; loss.backward(); optimizer.step() with ae_b200 modules (no step graph)"}
+
+
+def mlp_train_rate(dev, steps=200, batch=64):
+    """Second stage (NB:3475-3486): MLP steps on frozen 64-d latents, vectors/s, through the public fit helper's step."""
+    import ae_b200
+    from ae_b200 import fit
+    torch.manual_seed(0)
+    clf = ae_b200.MLP(64, 10).to(dev).train()
+    clf._state.prepare(dev, batch)
+    opt = ae_b200.Adam(clf.parameters(), lr=1e-4, weight_decay=1e-4)
+    n = batch * 64
+    X, y = torch.randn(n, 64, device=dev), torch.randint(0, 10, (n,), device=dev)
+    fit.train_epoch_mlp(clf, opt, X, y, batch, None)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = max(1, steps // 64)
+    for _ in range(reps):
+        fit.train_epoch_mlp(clf, opt, X, y, batch, None)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": reps * n / dt, "unit": "vectors/s", "batch": batch, "us_per_step": dt / (reps * 64) * 1e6}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -236,6 +236,9 @@ int tma_split_operand(const Operand& op, int64_t count, void* planes, int nsplit
 int run_bn_job(const BnJob& job, cudaStream_t st);   // the same job as stand-alone launches
 int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);   // p.A: AE_OP_SPLIT_BF16
 bool tma_rowgemm_supported(const RowGemm& p);
+// second-generation kernel for the training epilogues (rowgemm2.cu); tma_rowgemm dispatches to it
+bool rowgemm2_supported(const RowGemm& p);
+int tma_rowgemm2(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);
 bool tma_wgrad_supported(const Geom& g);
 int tma_wgrad_slices(const Geom& g);
 size_t tma_wgrad_partial_bytes(const Geom& g);

@@ -878,9 +878,18 @@ int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int bat
   AE_TRY(ae_encoder_backward(e, e->dz_tot, batch, stream));
   if (e->step_comm) {
     Part& E = e->part[AE_PART_ENC];
-    AE_TRY(ae_dp_allreduce(e->step_comm, E.grads, E.flat_len, st));
-    AE_CUDA(cudaEventRecord(e->ev_join2, e->side2));
-    AE_CUDA(cudaStreamWaitEvent(st, e->ev_join2, 0));
+    if (e->defer_conv1_wgrad) {
+      // captured step: every encoder gradient except conv1.weight (still to be computed) is final -- exchange them on the
+      // side branch, beside conv1's weight gradient; ae_step_graph_capture joins the branch before Adam reads them
+      const int64_t c1 = E.t[0].size;
+      AE_CUDA(cudaEventRecord(e->ev_fork2, st));
+      AE_CUDA(cudaStreamWaitEvent(e->side2, e->ev_fork2, 0));
+      AE_TRY(ae_dp_allreduce(e->step_comm, E.grads + c1, E.flat_len - c1, e->side2));
+    } else {
+      AE_TRY(ae_dp_allreduce(e->step_comm, E.grads, E.flat_len, st));
+      AE_CUDA(cudaEventRecord(e->ev_join2, e->side2));
+      AE_CUDA(cudaStreamWaitEvent(st, e->ev_join2, 0));
+    }
   }
   return 0;
 }
@@ -916,30 +925,50 @@ int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels,
   AE_CHECK(e && out && adam, "ae_step_graph_capture: null argument");
   AE_CHECK(st != nullptr, "ae_step_graph_capture: needs a non-default stream");
   AE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  // with a communicator the step exchanges its gradients itself (three sum-allreduces that together cover the flat
-  // gradient buffer, the first two overlapped with the encoder backward)
+  // with a communicator the step exchanges its gradients itself: sum-allreduces that together cover the flat gradient
+  // buffer, every one of them on a side branch beside compute (decoder + head beside the encoder backward, the encoder
+  // beside conv1's weight gradient, conv1.weight beside Adam + re-pack of everything else)
   e->step_comm = comm;
-  // Single GPU, tcgen05 path: conv1's weight gradient (the last 40 us of the backward pass, and the only gradient still
-  // missing) runs beside Adam + weight re-pack of every other parameter; its own 864 weights are updated after the join.
+  // tcgen05 path: conv1's weight gradient (the last 40 us of the backward pass, and the only gradient still missing) runs
+  // beside Adam + weight re-pack of every other parameter (single GPU) / beside the encoder's gradient exchange (data
+  // parallel); its own 864 weights are updated after the join.
   const int64_t c1 = 864;   // conv1.weight = the first tensor of the encoder part
-  const bool split_tail = !comm && !e->simt && e->part[AE_PART_ENC].params == flat_params && flat_len > c1;
+  const bool split_tail = !e->simt && e->part[AE_PART_ENC].params == flat_params && flat_len > c1;
   e->defer_conv1_wgrad = split_tail;
   int rc = ae_train_step(e, x, labels, batch, alpha, loss_out, stream);
   e->step_comm = nullptr;
   e->defer_conv1_wgrad = false;
   float gscale = 1.f;
   if (rc == 0 && comm) gscale = 1.f / (float)ae_dp_world(comm);
-  if (rc == 0 && split_tail) {
+  auto adam_range = [&](int64_t lo, int64_t n, int bump) {
+    return adam_step_flat_range(flat_params + lo, flat_grads + lo, adam_m + lo, adam_v + lo, n, adam->lr, adam->beta1, adam->beta2,
+                                adam->eps, adam->weight_decay, gscale, step_dev, bump, st);
+  };
+  auto link = [&](cudaEvent_t ev, cudaStream_t from, cudaStream_t to) {       // `to` continues after everything on `from`
+    if (cudaEventRecord(ev, from) != cudaSuccess || cudaStreamWaitEvent(to, ev, 0) != cudaSuccess) {
+      set_error("ae_step_graph_capture: event record / wait failed while capturing the data-parallel tail");
+      return 1;
+    }
+    return 0;
+  };
+  if (rc == 0 && split_tail && comm) {
+    rc = conv1_wgrad(e, batch, st);
+    // every exchange issued so far (decoder, head, encoder without conv1.weight) is complete before Adam reads it
+    if (rc == 0) rc = link(e->ev_join2, e->side2, st);
+    // conv1.weight's gradient travels beside Adam + re-pack of all other parameters
+    if (rc == 0) rc = link(e->ev_fork2, st, e->side2);
+    if (rc == 0) rc = ae_dp_allreduce(comm, flat_grads, c1, e->side2);
+    if (rc == 0) rc = adam_range(c1, flat_len - c1, 0);
+    if (rc == 0) rc = pack_all_parts(e, st);
+    if (rc == 0) rc = link(e->ev_join2, e->side2, st);
+    if (rc == 0) rc = adam_range(0, c1, 1);
+  } else if (rc == 0 && split_tail) {
     rc = fork_side(e, st);
     if (rc == 0) rc = conv1_wgrad(e, batch, e->side);
-    if (rc == 0)
-      rc = adam_step_flat_range(flat_params + c1, flat_grads + c1, adam_m + c1, adam_v + c1, flat_len - c1, adam->lr, adam->beta1,
-                                adam->beta2, adam->eps, adam->weight_decay, gscale, step_dev, 0, st);
+    if (rc == 0) rc = adam_range(c1, flat_len - c1, 0);
     if (rc == 0) rc = pack_all_parts(e, st);
     if (rc == 0) rc = join_side(e, st);
-    if (rc == 0)
-      rc = adam_step_flat_range(flat_params, flat_grads, adam_m, adam_v, c1, adam->lr, adam->beta1, adam->beta2, adam->eps,
-                                adam->weight_decay, gscale, step_dev, 1, st);
+    if (rc == 0) rc = adam_range(0, c1, 1);
   } else {
     if (rc == 0)
       rc = adam_step_flat(flat_params, flat_grads, adam_m, adam_v, flat_len, adam->lr, adam->beta1, adam->beta2, adam->eps,

@@ -58,6 +58,12 @@ def shard_bounds(total: int, rank: int, world: int):
 
 
 def broadcast_parameters(model, src: int = 0):
-    """Make every rank start from rank `src`'s parameters and buffers (torch.distributed plumbing)."""
+    """Make every rank start from rank `src`'s parameters and buffers (torch.distributed plumbing).  The writes go
+    through ``.data`` (no version bump), so the model's packed weights are invalidated explicitly: the next forward or
+    TrainStep re-derives them from the broadcast values."""
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src=src)
+    for m in model.modules():
+        eng = getattr(m, "_engine", None)
+        if eng is not None:
+            eng.invalidate()

@@ -99,6 +99,8 @@ class _Engine:
         self.step_off = {}
         self.packed_version = None
         self.instance = 0        # bumped whenever the native engine (and its workspace) is re-created
+        self.flat_instance = 0   # bumped whenever the flat parameter / gradient buffers are re-allocated
+        self.fwd_seq = {}        # part id -> sequence number of the last forward (its activations live in the workspace)
 
     def register(self, part: int, params: List[nn.Parameter], bns: List[nn.Module]):
         self.parts[part] = dict(params=params, bns=bns)
@@ -133,8 +135,14 @@ class _Engine:
         base = self.workspace.data_ptr()
         self.ws_ptr = C.c_void_p((base + 255) & ~255)
         check(lib.ae_engine_bind_workspace(h, self.ws_ptr, nbytes))
-        self.flat = None
+        # the flat parameter / gradient buffers (and with them every optimizer's moments) survive the re-creation: only
+        # the workspace and the native handle are new
+        if self.flat is not None and self.flat.data.device == device and self.flat.aliased() and self._buffers_aliased():
+            self._bind_parts()
+        else:
+            self.flat = None
         self.packed_version = None
+        self.fwd_seq = {}
 
     def _flatten(self):
         lib = _lib.load()
@@ -165,6 +173,7 @@ class _Engine:
             run_total += 2 * sum(layouts[part])
             step_total += nb
         self.flat = _Flat(params, offsets, total, self.device)
+        self.flat_instance += 1
         self.running = torch.zeros(max(run_total, 4), dtype=torch.float32, device=self.device)
         self.steps = torch.zeros(max(step_total, 1), dtype=torch.int64, device=self.device)
         with torch.no_grad():
@@ -179,6 +188,11 @@ class _Engine:
                     bn._buffers["running_var"] = self.running[ro + c:ro + 2 * c]
                     bn._buffers["num_batches_tracked"] = self.steps[so + i]
                     ro += 2 * c
+        self._bind_parts()
+        self.packed_version = None
+
+    def _bind_parts(self):
+        lib = _lib.load()
         for part in sorted(self.parts):
             po = self.part_off[part]
             has_bn = len(self.parts[part]["bns"]) > 0
@@ -187,7 +201,6 @@ class _Engine:
                 C.c_void_p(self.flat.grad.data_ptr() + 4 * po),
                 C.c_void_p(self.running.data_ptr() + 4 * self.run_off[part]) if has_bn else None,
                 C.c_void_p(self.steps.data_ptr() + 8 * self.step_off[part]) if has_bn else None))
-        self.packed_version = None
 
     def _buffers_aliased(self) -> bool:
         for part in self.parts:
@@ -217,14 +230,33 @@ class _Engine:
     def mark_packed(self):
         self.packed_version = self.flat.version_sum()
 
+    def invalidate(self):
+        """Call after changing parameters in a way torch's version counters do not see (``p.data.copy_(...)``,
+        ``dist.broadcast(p.data)``): the next forward re-derives the packed weights."""
+        if self.flat is not None:
+            self.flat.generation += 1
 
-def _part_views(engine: _Engine, part: int, flat_src: torch.Tensor):
+    # -- forward / backward pairing: the activations of a forward live in the engine's workspace, not in ctx -------------
+    def stamp_forward(self, part: int) -> int:
+        self.fwd_seq[part] = self.fwd_seq.get(part, 0) + 1
+        return self.fwd_seq[part]
+
+    def check_backward(self, part: int, seq: int, what: str):
+        if self.fwd_seq.get(part) != seq:
+            raise RuntimeError(
+                f"ae_b200: backward of a {what} forward whose activations are gone: another forward of the same module ran in "
+                "between (the engine keeps ONE set of activations per module; run backward before the next forward, e.g. no "
+                "gradient accumulation over two forwards and no retained graphs)")
+
+
+def _part_grads(engine: "_Engine", part: int):
+    """Snapshot of one part's slice of the flat gradient buffer as per-parameter views (autograd accumulates what a
+    Function returns, so the engine's own buffer must not be handed out)."""
     plist = engine.parts[part]["params"]
-    res = []
-    for p in plist:
-        _, off = p._ae_flat
-        res.append(flat_src[off:off + p.numel()].view(p.shape))
-    return res
+    lo = plist[0]._ae_flat[1]
+    hi = plist[-1]._ae_flat[1] + plist[-1].numel()
+    snap = engine.flat.grad[lo:hi].clone()
+    return [snap[p._ae_flat[1] - lo:p._ae_flat[1] - lo + p.numel()].view(p.shape) for p in plist]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -248,21 +280,26 @@ class _EncoderFn(torch.autograd.Function):
             for i in range(0, b, n):
                 m = min(n, b - i)
                 check(lib.ae_encoder_forward(engine.handle, ptr(x[i:i + m]), m, 0, ptr(z[i:i + m]), stream_ptr()))
-            ctx.engine, ctx.b = engine, b
+            engine.stamp_forward(_lib.PART_ENC)
+            ctx.mark_non_differentiable(z)         # only the last chunk's activations exist: inference only
             return z
         engine.prepare(x.device, b)
         check(_lib.load().ae_encoder_forward(engine.handle, ptr(x), b, int(training), ptr(z), stream_ptr()))
-        ctx.engine, ctx.b = engine, b
+        ctx.engine, ctx.b, ctx.training = engine, b, training
+        ctx.seq = engine.stamp_forward(_lib.PART_ENC)
         ctx.save_for_backward(x)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         engine = ctx.engine
+        if not ctx.training:
+            raise RuntimeError("ae_b200: backward through an eval-mode encoder forward is not supported (the engine keeps "
+                               "batch statistics only in training mode); call .train() or wrap the forward in no_grad()")
+        engine.check_backward(_lib.PART_ENC, ctx.seq, "encoder")
         dz = dz.contiguous()
         check(_lib.load().ae_encoder_backward(engine.handle, ptr(dz), ctx.b, stream_ptr()))
-        snap = engine.flat.grad.clone()
-        grads = _part_views(engine, _lib.PART_ENC, snap)
+        grads = _part_grads(engine, _lib.PART_ENC)
         grads = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[3:])]
         return (None, None, None, *grads)
 
@@ -276,18 +313,22 @@ class _DecoderFn(torch.autograd.Function):
         engine.prepare(z.device, b)
         x_hat = torch.empty(b, 3, 64, 64, dtype=torch.float32, device=z.device)
         check(_lib.load().ae_decoder_forward(engine.handle, ptr(z), b, int(training), ptr(x_hat), stream_ptr()))
-        ctx.engine, ctx.b = engine, b
+        ctx.engine, ctx.b, ctx.training = engine, b, training
+        ctx.seq = engine.stamp_forward(_lib.PART_DEC)
         ctx.save_for_backward(z)
         return x_hat
 
     @staticmethod
     def backward(ctx, d_xhat):
         engine = ctx.engine
+        if not ctx.training:
+            raise RuntimeError("ae_b200: backward through an eval-mode decoder forward is not supported; call .train() or "
+                               "wrap the forward in no_grad()")
+        engine.check_backward(_lib.PART_DEC, ctx.seq, "decoder")
         d_xhat = d_xhat.contiguous()
         dz = torch.empty(ctx.b, engine.latent_dim, dtype=torch.float32, device=d_xhat.device)
         check(_lib.load().ae_decoder_backward(engine.handle, ptr(d_xhat), ctx.b, ptr(dz), stream_ptr()))
-        snap = engine.flat.grad.clone()
-        grads = _part_views(engine, _lib.PART_DEC, snap)
+        grads = _part_grads(engine, _lib.PART_DEC)
         grads = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[3:])]
         return (dz if ctx.needs_input_grad[0] else None, None, None, *grads)
 
@@ -302,17 +343,18 @@ class _HeadFn(torch.autograd.Function):
         logits = torch.empty(b, engine.num_classes, dtype=torch.float32, device=z.device)
         check(_lib.load().ae_head_forward(engine.handle, ptr(z), b, ptr(logits), stream_ptr()))
         ctx.engine, ctx.b = engine, b
+        ctx.seq = engine.stamp_forward(_lib.PART_HEAD)
         ctx.save_for_backward(z)
         return logits
 
     @staticmethod
     def backward(ctx, d_logits):
         engine = ctx.engine
+        engine.check_backward(_lib.PART_HEAD, ctx.seq, "classifier-head")
         d_logits = d_logits.contiguous()
         dz = torch.empty(ctx.b, engine.latent_dim, dtype=torch.float32, device=d_logits.device)
         check(_lib.load().ae_head_backward(engine.handle, ptr(d_logits), ctx.b, ptr(dz), stream_ptr()))
-        snap = engine.flat.grad.clone()
-        grads = _part_views(engine, _lib.PART_HEAD, snap)
+        grads = _part_grads(engine, _lib.PART_HEAD)
         grads = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[2:])]
         return (dz if ctx.needs_input_grad[0] else None, None, *grads)
 
@@ -426,6 +468,8 @@ class SupervisedAutoencoder(nn.Module):
         loss = torch.empty(4, dtype=torch.float32, device=imgs.device)
         check(_lib.load().ae_train_step(eng.handle, ptr(imgs), ptr(labels.contiguous()), b, float(alpha), ptr(loss),
                                         stream_ptr()))
+        for part in (_lib.PART_ENC, _lib.PART_DEC, _lib.PART_HEAD):
+            eng.stamp_forward(part)
         for p, off in zip(eng.flat.params, eng.flat.offsets):
             if p.requires_grad:
                 p.grad = eng.flat.grad[off:off + p.numel()].view(p.shape)
@@ -446,6 +490,8 @@ class SupervisedAutoencoder(nn.Module):
         z = torch.empty(b, self.latent_dim, dtype=torch.float32, device=dev)
         check(_lib.load().ae_eval_step(eng.handle, ptr(imgs), ptr(labels.contiguous()), b, float(alpha), ptr(loss),
                                        ptr(x_hat), ptr(logits), ptr(z), stream_ptr()))
+        for part in (_lib.PART_ENC, _lib.PART_DEC, _lib.PART_HEAD):
+            eng.stamp_forward(part)
         return loss[:3], x_hat, logits, z
 
 

@@ -11,6 +11,7 @@ produced by the autograd path and are not already the flat gradient buffer).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -23,7 +24,7 @@ class Adam(torch.optim.Optimizer):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self._flat_state = {}     # id(flat) -> dict(m, v, step)
+        self._flat_state = weakref.WeakKeyDictionary()   # flat buffer object -> dict(m, v, step); dies with the buffer
         self.grad_scale = 1.0     # data parallel: 1/world after a sum-allreduce
         self._on_step = []        # callbacks run after the parameters changed (weight re-pack)
 
@@ -38,12 +39,12 @@ class Adam(torch.optim.Optimizer):
         return list(flats.values())
 
     def flat_state(self, flat):
-        st = self._flat_state.get(id(flat))
+        st = self._flat_state.get(flat)
         if st is None:
             dev = flat.data.device
             st = dict(m=torch.zeros_like(flat.data), v=torch.zeros_like(flat.data),
                       step=torch.zeros(2, dtype=torch.int32, device=dev))
-            self._flat_state[id(flat)] = st
+            self._flat_state[flat] = st
         return st
 
     @torch.no_grad()
@@ -59,36 +60,32 @@ class Adam(torch.optim.Optimizer):
                 base = flat.grad.data_ptr()
                 # gradients produced by autograd live elsewhere: gather them into the flat gradient buffer
                 srcs, dsts = [], []
-                covered = 0
+                stepped = set()
                 for p, off in plist:
                     n = p.numel()
-                    covered += n
                     g = p.grad
-                    dst = flat.grad[off:off + n]
                     if g is None:
-                        dst.zero_()
-                    elif g.data_ptr() != base + 4 * off or not g.is_contiguous():
+                        continue          # torch.optim.Adam skips parameters without a gradient: frozen for this step
+                    stepped.add(id(p))
+                    if g.data_ptr() != base + 4 * off or not g.is_contiguous():
                         srcs.append(g.reshape(-1))
-                        dsts.append(dst)
+                        dsts.append(flat.grad[off:off + n])
                 if srcs:
                     torch._foreach_copy_(dsts, srcs)
-                if len(plist) != len(flat.params):
-                    # frozen / foreign parameters of the same buffer must not move: zero their gradient and
-                    # protect them by restoring afterwards
-                    keep = [(q, o, q.detach().clone()) for q, o in zip(flat.params, flat.offsets)
-                            if all(q is not p for p, _ in plist)]
-                else:
-                    keep = []
+                # the kernel walks the whole flat buffer: parameters that must not move (no gradient this step, frozen, or
+                # not in this group) are restored afterwards together with their moments
+                keep = [(o, q.numel(), q.detach().clone(), st["m"][o:o + q.numel()].clone(), st["v"][o:o + q.numel()].clone())
+                        for q, o in zip(flat.params, flat.offsets) if id(q) not in stepped]
                 b1, b2 = group["betas"]
                 check(lib.ae_adam_step_flat(ptr(flat.data), ptr(flat.grad), ptr(st["m"]), ptr(st["v"]), flat.len,
                                             float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                             float(group["weight_decay"]), float(self.grad_scale), ptr(st["step"]),
                                             stream_ptr()))
                 flat.generation += 1
-                for q, o, val in keep:
-                    flat.data[o:o + q.numel()].copy_(val.reshape(-1))
-                    st["m"][o:o + q.numel()].zero_()
-                    st["v"][o:o + q.numel()].zero_()
+                for o, n, val, m0, v0 in keep:
+                    flat.data[o:o + n].copy_(val.reshape(-1))
+                    st["m"][o:o + n].copy_(m0)
+                    st["v"][o:o + n].copy_(v0)
         for cb in self._on_step:
             cb()
         return loss

@@ -43,7 +43,7 @@ class TrainStep:
         self.handle = h
         self.stream.synchronize()
         self._eng = eng
-        self._instance = eng.instance
+        self._instance = (eng.instance, eng.flat_instance)
         self.num_kernels = lib.ae_step_graph_num_kernels(h)
 
     def load(self, imgs: torch.Tensor, labels: torch.Tensor):
@@ -54,13 +54,15 @@ class TrainStep:
 
     def run(self, stream=None):
         """Replay the captured step on `stream` (default: this TrainStep's own stream)."""
-        if self._eng.instance != self._instance:
-            # the captured graph addresses the workspace of the engine it was captured on
-            raise RuntimeError("ae_b200: the model's engine was re-created (a larger batch was run through it) after this "
-                               "TrainStep was captured; build a new TrainStep")
+        if (self._eng.instance, self._eng.flat_instance) != self._instance:
+            # the captured graph addresses the workspace and the flat buffers of the engine it was captured on
+            raise RuntimeError("ae_b200: the model's engine or parameter storage was re-created (a larger batch was run "
+                               "through it, or the model was moved) after this TrainStep was captured; build a new TrainStep")
         check(_lib.load().ae_step_graph_launch(self.handle, C.c_void_p((stream or self.stream).cuda_stream)))
         self._eng.flat.generation += 1
         self._eng.mark_packed()      # the graph re-packs the weights itself
+        for part in (_lib.PART_ENC, _lib.PART_DEC, _lib.PART_HEAD):
+            self._eng.stamp_forward(part)   # the workspace now holds this step's activations
 
     def __call__(self, imgs, labels):
         """One step with torch stream semantics: inputs produced on the current stream are waited for, and the
@@ -78,7 +80,9 @@ class TrainStep:
         the loss of batch i is read back (D2H, pinned) while batch i+1 runs.  Every batch is copied host->device and
         every loss device->host; nothing is skipped.  Returns the list of [loss, mse, ce] host tensors."""
         dev = self.device
-        if not hasattr(self, "_copy_stream"):
+        if depth < 2:
+            raise ValueError("TrainStep.run_batches: depth must be >= 2 (one staging slot is filled while the other is read)")
+        if not hasattr(self, "_copy_stream") or len(self._stage) != depth:
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._stage = [(torch.empty_like(self.x), torch.empty_like(self.y)) for _ in range(depth)]
             self._staged = [torch.cuda.Event() for _ in range(depth)]

@@ -1,7 +1,8 @@
 """Load the reference's own model classes by executing its notebook cells.  TEST INFRASTRUCTURE.
 
-Works only where ``/root/reference`` is mounted (this build container, not the GPU box).
-Nothing is copied: the four class cells (NB:499-525 Encoder, NB:607-635 Decoder,
+Looks for the notebook under ``$AE_REFERENCE_ROOT``, ``/root/reference`` (this build container) and ``baseline/_ref``
+(the git-ignored copy ``__graft_entry__.build()`` places there so that it travels to the GPU box).
+Nothing is copied into the product: the four class cells (NB:499-525 Encoder, NB:607-635 Decoder,
 NB:685-702 SupervisedAutoencoder, NB:2970-2987 MLP) are read from the .ipynb at run time and
 ``exec``-ed into a namespace that holds only ``torch`` and ``nn``.
 """
@@ -11,12 +12,22 @@ import glob
 import json
 import os
 
-REFERENCE_ROOT = os.environ.get("AE_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE_ROOTS = [r for r in (os.environ.get("AE_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")) if r]
+REFERENCE_ROOT = REFERENCE_ROOTS[0]
 _WANTED = ("class Encoder(", "class Decoder(", "class SupervisedAutoencoder(", "class MLP(")
 
 
+def notebook_path():
+    for root in REFERENCE_ROOTS:
+        paths = sorted(glob.glob(os.path.join(root, "Code", "*.ipynb")))
+        if paths:
+            return paths[0]
+    return None
+
+
 def reference_available() -> bool:
-    return bool(glob.glob(os.path.join(REFERENCE_ROOT, "Code", "*.ipynb")))
+    return notebook_path() is not None
 
 
 def load_reference_classes():
@@ -24,9 +35,10 @@ def load_reference_classes():
     import torch
     import torch.nn as nn
 
-    paths = glob.glob(os.path.join(REFERENCE_ROOT, "Code", "*.ipynb"))
-    if not paths:
-        raise FileNotFoundError(f"reference notebook not found under {REFERENCE_ROOT}")
+    path = notebook_path()
+    if path is None:
+        raise FileNotFoundError(f"reference notebook not found under any of {REFERENCE_ROOTS}")
+    paths = [path]
     with open(paths[0], "r", encoding="utf-8") as f:
         nb = json.load(f)
     ns = {"torch": torch, "nn": nn}

@@ -4,7 +4,7 @@
 set -u
 TAG=$1; PREC=${2:-fp32}
 OUT=gpurun_out; mkdir -p $OUT
-CMD="python scratch/prof_all.py $PREC"
+CMD="python scripts/prof_all.py $PREC"
 $CMD > $OUT/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/${TAG}_plain.log; exit 1; }
 timeout 800 ncu --set full --clock-control none --profile-from-start off -o $OUT/${TAG}_all $CMD > $OUT/${TAG}_ncu_all.log 2>&1
 echo "ncu all rc=$?"; tail -2 $OUT/${TAG}_ncu_all.log

@@ -5,7 +5,7 @@
 set -u
 TAG=$1; PREC=${2:-fp32}
 OUT=gpurun_out; mkdir -p $OUT
-CMD="python scratch/prof_mix.py $PREC"
+CMD="python scripts/prof_mix.py $PREC"
 $CMD > $OUT/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/${TAG}_plain.log; exit 1; }
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_thin" -c 14 -o $OUT/${TAG}_thin $CMD > $OUT/${TAG}_ncu_thin.log 2>&1
 echo "ncu thin rc=$?"

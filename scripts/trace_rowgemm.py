@@ -53,9 +53,10 @@ def run(family, B, hs, cb, cs, epi_mode, prec="fp32", reps=5):
     op = _lib.Operand(_lib.ptr(planes), None, None, 0.0, _lib.OP_SPLIT_BF16)
     fn = lib.ae_conv2d_s2_dgrad if family == "dgrad" else lib.ae_conv2d_s2_fwd
     pk = pk_d if family == "dgrad" else pk_f
-    trace = torch.zeros(1024 * 16, dtype=torch.int64, device=dev)
-    lib.ae_debug_set_trace.argtypes = [C.c_void_p]
-    lib.ae_debug_set_trace.restype = C.c_int
+    trace = torch.zeros(1024 * 16 + 512, dtype=torch.int64, device=dev)
+    for fnn in ("ae_debug_set_trace", "ae_debug_set_trace2"):       # first / second generation kernel: only one of them runs
+        getattr(lib, fnn).argtypes = [C.c_void_p]
+        getattr(lib, fnn).restype = C.c_int
     flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)
     for cold in (False, True):
         rows = []
@@ -65,13 +66,16 @@ def run(family, B, hs, cb, cs, epi_mode, prec="fp32", reps=5):
             trace.zero_()
             torch.cuda.synchronize()
             assert lib.ae_debug_set_trace(C.c_void_p(trace.data_ptr())) == 0
+            assert lib.ae_debug_set_trace2(C.c_void_p(trace.data_ptr())) == 0
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             _lib.check(fn(C.byref(g), C.byref(op), pk, C.byref(ep), _lib.ptr(out), P, _lib.BACKEND_TC, _lib.stream_ptr()))
             e1.record()
             torch.cuda.synchronize()
-            t = trace.view(-1, 16).cpu()
+            t = trace[:16384].view(-1, 16).cpu()
             t = t[t[:, 0] > 0]
+            items = trace[16384:16384 + 240].view(-1, 4).cpu()
+            prod = trace[16384 + 256:16384 + 256 + 240].view(-1, 4).cpu()
             rows.append((e0.elapsed_time(e1) * 1e3, t))
         us, t = rows[-1]
         t0 = int(t[:, 0].min())
@@ -84,7 +88,15 @@ def run(family, B, hs, cb, cs, epi_mode, prec="fp32", reps=5):
             col = col[t[:, i] > 0]
             if col.numel():
                 print(f"    {name:11s} {float(col.min()):7.2f} {float(col.median()):9.2f} {float(col.max()):7.2f}")
-        assert lib.ae_debug_set_trace(None) == 0
+        it, pr = items.view(-1), prod.view(-1)
+        if int(it[3]) > 0:      # second-generation kernel, CTA 0: cycle accounting of the two single-thread roles
+            mhz = float(it[3]) / max(float(it[4]), 1.0) * 1e3
+            n = max(int(it[5]), 1)
+            print(f"    CTA0 MMA thread: {int(it[5])} A items, {int(it[3])} clk total at {mhz:.0f} MHz; per item: wait A {int(it[0]) / n:.0f} clk, "
+                  f"wait W {int(it[1]) / n:.0f}, issue {int(it[2]) / n:.0f}, other {(int(it[3]) - int(it[0]) - int(it[1]) - int(it[2])) / n:.0f}")
+            print(f"    CTA0 producer: {int(pr[2])} clk total; per item: wait A slot {int(pr[0]) / n:.0f} clk, wait W slot {int(pr[1]) / n:.0f}, "
+                  f"other {(int(pr[2]) - int(pr[0]) - int(pr[1])) / n:.0f}")
+        assert lib.ae_debug_set_trace(None) == 0 and lib.ae_debug_set_trace2(None) == 0
 
 
 if __name__ == "__main__":
@@ -93,9 +105,10 @@ if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     which = sys.argv[2] if len(sys.argv) > 2 else "all"
     run("dgrad", B, 8, 64, 128, "bias_stats")       # ConvTranspose2d 128->64 forward (the roofline kernel)
-    run("dgrad", B, 8, 64, 128, "relubwd")          # Conv2d 64->128 data gradient
+    run("fprop", B, 16, 32, 64, "bias_stats")       # Conv2d 32->64 forward
     run("fprop", B, 4, 128, 256, "bias_stats")      # Conv2d 128->256 forward
     if which == "all":
+        run("dgrad", B, 8, 64, 128, "relubwd")          # Conv2d 64->128 data gradient
         run("dgrad", B, 8, 64, 128, "store")
         run("dgrad", B, 16, 32, 64, "bias_stats")       # ConvTranspose2d 64->32 forward
         run("dgrad", B, 4, 128, 256, "bias_stats")      # ConvTranspose2d 256->128 forward

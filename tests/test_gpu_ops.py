@@ -193,7 +193,11 @@ def test_conv_fused_bnrelu_split_epilogue(shape, family, prec):
     epf = gu.epilogue(_lib.EPI_BNRELU_SPLIT, biasd, None, bncd)
     _lib.check(fn(C.byref(g), C.byref(op), gu.p(pk), C.byref(epf), gu.p(got), gu.PREC[prec], gu.BACK["tc"], gu.stream()))
     torch.cuda.synchronize()
-    assert torch.equal(got, want), "fused epilogue planes differ from the two-pass planes"
+    # the training-mode launch (second-generation kernel) accumulates the taps in another order than the fused one: equal up
+    # to fp32 rounding of the accumulator, i.e. the decoded planes agree to ~2^-17 (one bf16 ulp in bf16 mode)
+    gv, wv = _decode_planes(got, (b, hout, hout, cout), prec), _decode_planes(want, (b, hout, hout, cout), prec)
+    assert float((gv - wv).abs().max()) <= (2e-5 if prec == "fp32" else 8e-3) * float(wv.abs().max()), \
+        "fused epilogue planes differ from the two-pass planes"
     # and against the CPU reference of the layer
     if family == "fwd":
         ref = F.conv2d(a, w, bias, stride=2, padding=1)
