@@ -186,7 +186,7 @@ def cpu_train_steps(batch, steps, warmup):
         step(x, y)
     t0 = time.perf_counter()
     for _ in range(steps):
-        float(step(x, y))                                     # NB:2687: loss.item() every step
+        step(x, y).item()                                     # NB:2687: loss.item() every step
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps, kind, what
 
@@ -270,12 +270,12 @@ def mlp_train_rate(dev, steps=200, batch=64):
     opt = ae_b200.Adam(clf.parameters(), lr=1e-4, weight_decay=1e-4)
     n = batch * 64
     X, y = torch.randn(n, 64, device=dev), torch.randint(0, 10, (n,), device=dev)
-    fit.train_epoch_mlp(clf, opt, X, y, batch, None)
+    fit.train_epoch_mlp(clf, opt, X, y, batch, True, None)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     reps = max(1, steps // 64)
     for _ in range(reps):
-        fit.train_epoch_mlp(clf, opt, X, y, batch, None)
+        fit.train_epoch_mlp(clf, opt, X, y, batch, True, None)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return {"value": reps * n / dt, "unit": "vectors/s", "batch": batch, "us_per_step": dt / (reps * 64) * 1e6}
@@ -288,13 +288,22 @@ def mlp_train_rate(dev, steps=200, batch=64):
 # rotating over more buffers than fit in L2.  Algorithmic bytes per launch: the operand
 # planes once + the packed weights once + the fp32 output once.
 # --------------------------------------------------------------------------------------------------
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1_v6_roofline_kernel_full.txt (ncu --set full of this
-# very loop): 8.73 MB read = the operand planes + weights, exactly the algorithmic reads; 0 written inside the kernel's window
-# (the 16.8 MB output is still dirty in the 126 MB L2 when the kernel ends)
-TRAFFIC_NCU = {"fp32": 8.73e6, "bf16": None}
+def measured_traffic(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this very kernel from the round's `ncu --set full` capture
+    (profiles/r2_roofline_traffic.json, written by scripts/ncu_summary.py from the .ncu-rep); None when no capture of the
+    current kernel generation has been committed."""
+    p = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
+    try:
+        return json.load(open(p)).get(precision)
+    except Exception:
+        return None
 
 
-def kernel_roofline(dev, B, precision, iters=60):
+def kernel_roofline(dev, B, precision, replays=20):
+    """The dominant kernel on its own: ConvTranspose2d 128->64 forward (NB:620, 8x8 -> 16x16 pixels) at batch B through the
+    C ABI.  The launches are captured ONCE into a CUDA graph (one launch per buffer set, rotating over more sets than fit
+    in L2) and the graph is replayed between CUDA events on the launching stream: the average is device time per launch,
+    launch gaps included, host-side tensor-map encoding excluded."""
     import ctypes as C
     from ae_b200 import _lib
     lib = _lib.load()
@@ -316,29 +325,41 @@ def kernel_roofline(dev, B, precision, iters=60):
     planes = [(torch.randn(nsplit * M * cs, device=dev) * 0.5).to(torch.bfloat16) for _ in range(n_rot)]
     outs = [torch.empty(B, 2 * hs, 2 * hs, cb, device=dev) for _ in range(n_rot)]
     ep = _lib.Epilogue(_lib.EPI_BIAS_STATS, _lib.ptr(bias), None, None, _lib.ptr(stats))
+    st = torch.cuda.Stream(device=dev)
 
     def launch(i):
         op = _lib.Operand(_lib.ptr(planes[i % n_rot]), None, None, 0.0, _lib.OP_SPLIT_BF16)
         _lib.check(lib.ae_conv2d_s2_dgrad(C.byref(g), C.byref(op), pk_d, C.byref(ep), _lib.ptr(outs[i % n_rot]), prec,
-                                          _lib.BACKEND_TC, _lib.stream_ptr()))
+                                          _lib.BACKEND_TC, C.c_void_p(st.cuda_stream)))
 
-    for i in range(5):
-        launch(i)
     torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    for i, (e0, e1) in enumerate(evs):
-        e0.record()
-        launch(i)
-        e1.record()
-    torch.cuda.synchronize()
-    ts = sorted(e0.elapsed_time(e1) * 1e-3 for e0, e1 in evs)
+    with torch.cuda.stream(st):
+        for i in range(n_rot):
+            launch(i)
+        st.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            for i in range(n_rot):
+                launch(i)
+        for _ in range(3):
+            graph.replay()
+        st.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(replays)]
+        for e0, e1 in evs:
+            e0.record(st)
+            graph.replay()
+            e1.record(st)
+        st.synchronize()
+    ts = sorted(e0.elapsed_time(e1) * 1e-3 / n_rot for e0, e1 in evs)
     t = sum(ts) / len(ts)
     peaks = measured_peaks()
     alg = a_bytes + o_bytes + w_bytes
     flop = 2.0 * M * 9 * cs * cb
     return {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "frac": alg / t / 1e9 / peaks["hbm"],
-            "traffic": TRAFFIC_NCU.get(precision), "kernel": "k_tma_rowgemm<DGRAD,NT=64> (ConvTranspose2d 128->64 forward, batch %d)" % B,
-            "algorithmic_bytes": alg, "avg_launch_us": t * 1e6, "median_launch_us": ts[len(ts) // 2] * 1e6, "launches_timed": iters,
+            "traffic": measured_traffic(precision),
+            "kernel": "second-generation row GEMM k_rowgemm2<DGRAD,64> (ConvTranspose2d 128->64 forward, batch %d)" % B,
+            "algorithmic_bytes": alg, "avg_launch_us": t * 1e6, "median_launch_us": ts[len(ts) // 2] * 1e6,
+            "launches_timed": replays * n_rot, "timing": "CUDA-graph replays of %d back-to-back launches between CUDA events" % n_rot,
             "tensor_tflops": flop / t / 1e12, "tensor_frac_of_burst": flop / t / 1e12 / peaks["tf_burst"],
             "peak_source": peaks["source"], "l2": f"inputs/outputs rotate over {n_rot} buffer sets ({n_rot * (a_bytes + o_bytes) / 1e6:.0f} MB > L2)"}
 
@@ -383,6 +404,106 @@ def inference_rate(dev, precision, backend, batch=4096, iters=20, sweep=(1024, 4
 
 
 # --------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: data-parallel training at GLOBAL batch 4096 (4096 / world images per rank), and the
+# on-hardware parity check of the data-parallel step (per-rank BatchNorm statistics, gradients averaged).
+# --------------------------------------------------------------------------------------------------
+def dp_global_batch(dev, world, rank, comm, args, global_batch, steps=30, warmup=5):
+    import torch.distributed as dist
+    import ae_b200
+    b = global_batch // world
+    torch.manual_seed(0)
+    model = ae_b200.SupervisedAutoencoder(64, 10, precision=args.precision, backend=args.backend).to(dev).train()
+    model.engine().prepare(dev, b)
+    if world > 1:
+        ae_b200.dp.broadcast_parameters(model)
+    opt = ae_b200.Adam(model.parameters(), lr=LR)
+    stepper = ae_b200.TrainStep(model, opt, ALPHA, b, comm=comm)
+    n_rot = max(2, int(300e6 // (b * 49152)) + 1)             # distinct input bytes in rotation > 2 x L2
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    xs = [torch.rand(b, 3, 64, 64, device=dev, generator=g) for _ in range(n_rot)]
+    ys = [torch.randint(0, 10, (b,), device=dev, generator=g) for _ in range(n_rot)]
+
+    def run(k, i0):
+        for i in range(k):
+            stepper.load(xs[(i0 + i) % n_rot], ys[(i0 + i) % n_rot])
+            stepper.run()
+    run(warmup, 0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stepper.stream)
+    run(steps, warmup)
+    e1.record(stepper.stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    loss = float(stepper.loss[0])
+    stepper.close()
+    return {"workload": f"BASELINE configs[3]: data-parallel AE train step, GLOBAL batch {global_batch} = {b} per GPU x {world}",
+            "value": global_batch / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "batch_per_gpu": b, "n_gpus": world,
+            "scaling": "strong", "steps": steps, "kernels_per_step": int(stepper.num_kernels), "final_loss": loss,
+            "step_tflops": FLOP_PER_IMAGE_TRAIN * global_batch / (ms * 1e-3) / 1e12}
+
+
+def dp_gradient_check(dev, world, rank, comm, model, opt, stepper, xs_d, ys_d):
+    """One more data-parallel step, checked on rank 0 against the single-GPU path: gather every rank's shard, compute each
+    shard's gradient with `train_step_grads` on the same weights, average, and compare with (a) the gradient buffer the
+    captured step leaves behind (the NCCL sum) times 1/world and (b) the parameters after the step, predicted by torch's
+    Adam formula from the averaged gradient and the optimizer state before the step (this is what a wrong 1/world in the
+    fused Adam kernel would break)."""
+    import torch.distributed as dist
+    import ae_b200
+    eng = model.engine()
+    flat = eng.flat
+    st = opt.flat_state(flat)
+    B = xs_d[0].shape[0]
+    x, y = xs_d[rank % len(xs_d)], ys_d[rank % len(ys_d)]
+    torch.cuda.synchronize()
+    p0, m0, v0 = flat.data.clone(), st["m"].clone(), st["v"].clone()
+    step0 = int(st["step"][0])
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    stepper.load(x, y)
+    stepper.run()
+    torch.cuda.synchronize()
+    g_nccl = flat.grad.clone() / world
+    p1 = flat.data.clone()
+    gx = [torch.empty_like(x) for _ in range(world)]
+    gy = [torch.empty_like(y) for _ in range(world)]
+    dist.all_gather(gx, x)
+    dist.all_gather(gy, y)
+    out = None
+    if rank == 0:
+        ref = ae_b200.SupervisedAutoencoder(64, 10, precision=eng.precision, backend=eng.backend).to(dev).train()
+        acc = torch.zeros(flat.len, dtype=torch.float64, device=dev)
+        for r in range(world):
+            ref.load_state_dict(state0)
+            ref.train_step_grads(gx[r], gy[r], ALPHA)
+            acc += ref.engine().flat.grad.double()
+        g_ref = (acc / world).float()
+        grad_rel = float((g_nccl - g_ref).norm() / g_ref.norm())
+        group = opt.param_groups[0]
+        b1, b2 = group["betas"]
+        t = step0 + 1
+        m = m0 + (g_ref - m0) * (1 - b1)
+        v = v0 * b2 + g_ref * g_ref * (1 - b2)
+        denom = v.sqrt() / (1 - b2 ** t) ** 0.5 + group["eps"]
+        p_pred = p0 - (group["lr"] / (1 - b1 ** t)) * (m / denom)
+        upd_rel = float((p1 - p_pred).norm() / (p_pred - p0).norm())
+        # the same prediction with the SUM instead of the mean: how far off a missing 1/world would be
+        ms_, vs_ = m0 + (g_ref * world - m0) * (1 - b1), v0 * b2 + (g_ref * world) ** 2 * (1 - b2)
+        p_bad = p0 - (group["lr"] / (1 - b1 ** t)) * (ms_ / (vs_.sqrt() / (1 - b2 ** t) ** 0.5 + group["eps"]))
+        out = {"grad_rel": grad_rel, "update_rel": upd_rel, "update_rel_if_scale_were_missing": float((p1 - p_bad).norm() / (p_bad - p0).norm()),
+               "world": world, "adam_step": t, "batch_per_gpu": int(B),
+               "what": "rel-L2 of NCCL gradient/world (and of the parameters after the captured step) against per-shard single-GPU gradients averaged on rank 0"}
+    dist.barrier()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
     import ae_b200
@@ -403,8 +524,7 @@ def run_ours(args):
     model = ae_b200.SupervisedAutoencoder(64, 10, precision=args.precision, backend=args.backend).to(dev).train()
     model.engine().prepare(dev, B)
     if world > 1:
-        ae_b200.dp.broadcast_parameters(model)
-        model.engine().pack()
+        ae_b200.dp.broadcast_parameters(model)          # also invalidates the weight packs: TrainStep re-derives them
     opt = ae_b200.Adam(model.parameters(), lr=LR)
     stepper = ae_b200.TrainStep(model, opt, ALPHA, B, comm=comm)
 
@@ -486,6 +606,25 @@ def run_ours(args):
     roof = None if args.no_roofline else kernel_roofline(dev, B, args.precision)
     infer = None if args.no_roofline else inference_rate(dev, args.precision, args.backend)
 
+    # ---- extras (reported, never the headline): stock PyTorch on this GPU, the drop-in loop, the MLP stage, and the
+    # data-parallel configuration BASELINE names (global batch 4096, strong scaling) with an on-hardware gradient check
+    extras = {}
+    if not args.no_extras:
+        def guarded(name, fn):
+            try:
+                extras[name] = fn()
+            except Exception as ex:                          # a reporting extra must never cost the headline
+                extras[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        if rank == 0 or world == 1:
+            guarded("torch_gpu_baseline", lambda: torch_gpu_baseline(dev, B, xs_d, ys_d))
+            guarded("dropin_loop", lambda: dropin_loop(dev, B, xs_d, ys_d, args.precision, args.backend))
+            guarded("mlp_train", lambda: mlp_train_rate(dev))
+        barrier()
+        guarded("dp_global_4096", lambda: dp_global_batch(dev, world, rank, comm, args, 4096))
+        if world > 1:
+            guarded("dp_check", lambda: dp_gradient_check(dev, world, rank, comm, model, opt, stepper, xs_d, ys_d))
+        barrier()
+
     peaks = measured_peaks()
     flops = FLOP_PER_IMAGE_TRAIN * B
     step_s = ms * 1e-3 / args.steps
@@ -511,13 +650,14 @@ def run_ours(args):
         line["roofline"] = roof
     if infer is not None:
         line["inference"] = infer
+    line.update(extras)
     if rank == 0 and not args.no_cpu_baseline and world == 1:      # N=1 only: other ranks' spin-waits would share the host cores
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         n = 12
-        ips, per = cpu_train_steps(B, n, 2)
-        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{n} train steps of batch {B} (oracle/torch_port.py, torch CPU fp32)"}
+        ips, per, kind, what = cpu_train_steps(B, n, 2)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": f"{n} train steps of batch {B} ({what}; torch CPU fp32)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -554,6 +694,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the stand-alone kernel timing and the inference leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the end-to-end leg (its number is then meaningless)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the torch-GPU baseline, drop-in loop, MLP and global-batch-4096 legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -237,7 +237,8 @@ int run_bn_job(const BnJob& job, cudaStream_t st);   // the same job as stand-al
 int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);   // p.A: AE_OP_SPLIT_BF16
 bool tma_rowgemm_supported(const RowGemm& p);
 // second-generation kernel for the training epilogues (rowgemm2.cu); tma_rowgemm dispatches to it
-bool rowgemm2_supported(const RowGemm& p);
+bool rowgemm2_supported(const RowGemm& p);   // shape + epilogue
+bool rowgemm2_preferred(const RowGemm& p);   // ... and measured to be the faster generation for this problem size
 int tma_rowgemm2(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);
 bool tma_wgrad_supported(const Geom& g);
 int tma_wgrad_slices(const Geom& g);

@@ -490,6 +490,11 @@ bool rowgemm2_supported(const RowGemm& p) {
   if (p.epi.planes != nullptr || p.out == nullptr) return false;
   if (p.N % 32 != 0 || p.N > (p.family == FAM_DGRAD ? 128 : 256)) return false;
   if (p.family == FAM_FPROP && p.N % 64 != 0) return false;
+  return true;
+}
+
+bool rowgemm2_preferred(const RowGemm& p) {
+  if (!rowgemm2_supported(p)) return false;
   // Measured against the first generation at batch 256 (scripts/rowgemm_bench.py, profiles/r2_rowgemm_gen1_vs_gen2.txt):
   // one CTA per SM needs ~100 tiles to win (ConvTranspose2d 256->128 at batch 256 has 64 merged tiles), and the 32-channel
   // K chunks of Conv2d(32,64) make 16 KB boxes whose per-box cost dominates.

@@ -544,10 +544,11 @@ int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t s
   AE_CHECK(tma_rowgemm_supported(p), "tma_rowgemm: unsupported shape");
   AE_CHECK(p.A.mode == AE_OP_SPLIT_BF16, "tma_rowgemm: the A operand must be split-bf16 planes (ae_split_operand)");
   AE_CHECK(((uintptr_t)packed & 15) == 0, "tma_rowgemm: packed weights must be 16-byte aligned");
-  // training epilogues go to the second-generation kernel (AE_B200_ROWGEMM_V1=1: A/B switch for measurements)
-  const char* v1_env = getenv("AE_B200_ROWGEMM_V1");
-  const bool force_v1 = v1_env != nullptr && atoi(v1_env) == 1;
-  if (!force_v1 && rowgemm2_supported(p)) return tma_rowgemm2(p, packed, nsplit, st);
+  // training epilogues go to the second-generation kernel where it is the faster one.  AE_B200_ROWGEMM=1 / 2: A/B switch
+  // for measurements and tests (1 = first generation always, 2 = second generation wherever it supports the problem)
+  const char* gen_env = getenv("AE_B200_ROWGEMM");
+  const int gen = gen_env ? atoi(gen_env) : 0;
+  if (gen != 1 && (gen == 2 ? rowgemm2_supported(p) : rowgemm2_preferred(p))) return tma_rowgemm2(p, packed, nsplit, st);
   TmaRow q;
   memset(&q, 0, sizeof(q));
   q.wtiles = (const uint8_t*)packed;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Developer tool: device time of every row-GEMM launch of one training step (batch B), first generation
-(AE_B200_ROWGEMM_V1=1) against second generation, each timed as a CUDA graph of back-to-back launches rotating over
+(AE_B200_ROWGEMM=1) against second generation, each timed as a CUDA graph of back-to-back launches rotating over
 more buffers than fit in L2 (host-side launch cost -- tensor-map encoding -- is outside the graph replay).
 
     python scripts/rowgemm_bench.py [B]
@@ -77,10 +77,10 @@ def case(family, B, hs, cb, cs, epi_mode, prec="fp32"):
         _lib.check(fn(C.byref(g), C.byref(op), pk, C.byref(ep), _lib.ptr(outs[i]), P, _lib.BACKEND_TC, C.c_void_p(st.cuda_stream)))
 
     res = []
-    for v1 in ("1", "0"):
-        os.environ["AE_B200_ROWGEMM_V1"] = v1
+    for gen in ("1", "2"):
+        os.environ["AE_B200_ROWGEMM"] = gen
         res.append(time_graph(launch, n_rot))
-    os.environ.pop("AE_B200_ROWGEMM_V1")
+    os.environ.pop("AE_B200_ROWGEMM")
     flop = 2.0 * Ms * 9 * cs * cb
     print(f"{family:6s} hs={hs:2d} cb={cb:3d} cs={cs:3d} {epi_mode:10s} {prec}: gen1 {res[0]:6.2f} us   gen2 {res[1]:6.2f} us   "
           f"({flop / res[1] / 1e6:6.1f} TFLOP/s useful, rot {n_rot})")

@@ -21,6 +21,15 @@ def _geom(b, hs, cb, cs):
     return _lib.ConvGeom(b, hs, hs, cb, cs)
 
 
+@pytest.fixture(params=["auto", "gen1", "gen2"])
+def rowgemm_gen(request, monkeypatch):
+    """Both generations of the tcgen05 row GEMM on every shape: "auto" is the library's own choice (the second generation
+    from ~100 tiles up), "gen2" forces the second generation wherever it supports the problem (AE_B200_ROWGEMM, read per call)."""
+    if request.param != "auto":
+        monkeypatch.setenv("AE_B200_ROWGEMM", request.param[-1])
+    return request.param
+
+
 def _apply_operand_cpu(mode, src, src2, bnc):
     """NCHW cpu tensors; bnc [8][C] cpu."""
     v = lambda r: bnc[r].view(1, -1, 1, 1)
@@ -35,9 +44,11 @@ def _apply_operand_cpu(mode, src, src2, bnc):
 @pytest.mark.parametrize("prec", gu.PRECISIONS)
 @pytest.mark.parametrize("mode", [_lib.OP_RAW, _lib.OP_BNRELU, _lib.OP_BNBWD])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_conv_fwd(shape, mode, prec, backend):
+def test_conv_fwd(shape, mode, prec, backend, rowgemm_gen):
     if backend == "simt" and prec == "bf16":
         pytest.skip("the CUDA-core backend always computes in fp32")
+    if backend == "simt" and rowgemm_gen != "auto":
+        pytest.skip("row-GEMM generations are a tcgen05-path switch")
     b, hs, cb, cs = shape
     rs = np.random.RandomState(hash((shape, mode)) % 2 ** 31)
     d = gu.dev()
@@ -70,9 +81,11 @@ def test_conv_fwd(shape, mode, prec, backend):
 @pytest.mark.parametrize("prec", gu.PRECISIONS)
 @pytest.mark.parametrize("mode", [_lib.OP_RAW, _lib.OP_BNRELU, _lib.OP_BNBWD])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_conv_dgrad_is_transposed_conv(shape, mode, prec, backend):
+def test_conv_dgrad_is_transposed_conv(shape, mode, prec, backend, rowgemm_gen):
     if backend == "simt" and prec == "bf16":
         pytest.skip("the CUDA-core backend always computes in fp32")
+    if backend == "simt" and rowgemm_gen != "auto":
+        pytest.skip("row-GEMM generations are a tcgen05-path switch")
     b, hs, cb, cs = shape
     rs = np.random.RandomState(hash((shape, mode, 1)) % 2 ** 31)
     d = gu.dev()
@@ -116,6 +129,18 @@ def test_conv_dgrad_is_transposed_conv(shape, mode, prec, backend):
     s2 = (ref_dz.double() * xhat.double()).sum(dim=(0, 2, 3))
     denom = float((ref_dz.double() * xhat.double()).abs().sum(dim=(0, 2, 3)).max())
     assert float((stats[cb:].cpu() - s2).abs().max()) <= gu.TOL[prec] * denom
+
+
+@pytest.mark.parametrize("prec", gu.PRECISIONS)
+@pytest.mark.parametrize("shape", [(300, 8, 64, 128), (80, 16, 32, 64), (150, 4, 128, 256), (301, 4, 128, 256)])
+def test_rowgemm_second_generation_many_tiles(shape, prec, monkeypatch):
+    """More tiles than SMs: every CTA of the second-generation kernel walks several tiles (double-buffered accumulators,
+    ring wrap-around, resident weight groups re-used across tiles, the 128-wide forward tiles), ragged last tile included."""
+    if "tc" not in gu.BACKENDS:
+        pytest.skip("tcgen05 path only")
+    monkeypatch.setenv("AE_B200_ROWGEMM", "2")
+    test_conv_fwd(shape, _lib.OP_RAW, prec, "tc", "gen2")
+    test_conv_dgrad_is_transposed_conv(shape, _lib.OP_BNRELU, prec, "tc", "gen2")
 
 
 @pytest.mark.parametrize("backend", gu.BACKENDS)
