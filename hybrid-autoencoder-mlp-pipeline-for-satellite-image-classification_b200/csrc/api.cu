@@ -24,14 +24,6 @@ int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias
 size_t thin_wgrad_workspace_bytes(int batch);
 int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
                    float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st, int phase);
-int thin_tc_gather_fwd(const Operand& thin, const float* w, const Epilogue& epi, float* out, int batch, int nsplit, cudaStream_t st);
-int thin_tc_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes, int batch,
-                  int nsplit, cudaStream_t st);
-int thin_tc_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
-                      float* dbias, void* partials, size_t bytes, int batch, int nsplit, cudaStream_t st);
-int thin_tc_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* bias, float* x_hat, const float* x,
-                                double* sse, int batch, int nsplit, cudaStream_t st);
-size_t thin_tc_wgrad_workspace_bytes(int batch);
 int bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float* rmean, float* rvar,
                 float* bnc, int C, int training, cudaStream_t st);
 int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta, int C,
@@ -152,8 +144,7 @@ int ae_conv2d_s2_wgrad(const ae_conv_geom_t* g, const ae_operand_t* big, const a
 int ae_thin_gather_fwd(const ae_operand_t* thin, const float* w, const ae_epilogue_t* epi, float* out_wide, int batch,
                        int precision, int backend, ae_stream_t stream) {
   AE_CHECK(thin && w && out_wide && batch >= 1, "ae_thin_gather_fwd: bad argument");
-  if (backend == AE_BACKEND_TC)
-    return thin_tc_gather_fwd(make_operand(thin, 3), w, make_epilogue(epi, 32), out_wide, batch, nsplit_of(precision), (cudaStream_t)stream);
+  (void)backend;                                      // both backends run the fp32 CUDA-core kernels (see ae_b200.h)
   Epilogue ep = make_epilogue(epi, 32);
   ep.nsplit = nsplit_of(precision);                   // AE_EPI_BNRELU_SPLIT: planes written
   return thin_gather_fwd(make_operand(thin, 3), w, ep, out_wide, batch, (cudaStream_t)stream);
@@ -162,22 +153,18 @@ int ae_thin_gather_fwd(const ae_operand_t* thin, const float* w, const ae_epilog
 int ae_thin_scatter_sigmoid_fwd(const ae_operand_t* wide, const float* w, const float* bias, float* x_hat, const float* x,
                                 double* sse, int batch, int precision, int backend, ae_stream_t stream) {
   AE_CHECK(wide && w && bias && x_hat && batch >= 1, "ae_thin_scatter_sigmoid_fwd: bad argument");
-  if (backend == AE_BACKEND_TC)
-    return thin_tc_scatter_sigmoid_fwd(make_operand(wide, 32), w, bias, x_hat, x, sse, batch, nsplit_of(precision), (cudaStream_t)stream);
+  (void)backend; (void)precision;
   return thin_scatter_sigmoid_fwd(make_operand(wide, 32), w, bias, x_hat, x, sse, batch, (cudaStream_t)stream);
 }
 
 size_t ae_thin_wgrad_workspace_bytes(int batch) {
-  const size_t a = thin_wgrad_workspace_bytes(batch), b = thin_tc_wgrad_workspace_bytes(batch);
-  return a > b ? a : b;
+  return thin_wgrad_workspace_bytes(batch);
 }
 
 int ae_thin_wgrad(const ae_operand_t* wide, const ae_operand_t* thin, float* dw, float* dbias_thin, void* partials,
                   size_t partials_bytes, int batch, int precision, int backend, ae_stream_t stream) {
   AE_CHECK(wide && thin && dw && partials && batch >= 1, "ae_thin_wgrad: bad argument");
-  if (backend == AE_BACKEND_TC)
-    return thin_tc_wgrad(make_operand(wide, 32), make_operand(thin, 3), dw, dbias_thin, partials, partials_bytes, batch,
-                         nsplit_of(precision), (cudaStream_t)stream);
+  (void)backend; (void)precision;
   return thin_wgrad(make_operand(wide, 32), make_operand(thin, 3), dw, dbias_thin, partials, partials_bytes, batch,
                     (cudaStream_t)stream);
 }
@@ -186,9 +173,7 @@ int ae_thin_bwd_fused(const ae_operand_t* wide, const ae_operand_t* thin, const 
                       float* out_wide, float* dw, float* dbias_thin, void* partials, size_t partials_bytes, int batch,
                       int precision, int backend, ae_stream_t stream) {
   AE_CHECK(wide && thin && w && epi && out_wide && dw && partials && batch >= 1, "ae_thin_bwd_fused: bad argument");
-  if (backend == AE_BACKEND_TC)
-    return thin_tc_bwd_fused(make_operand(wide, 32), make_operand(thin, 3), w, make_epilogue(epi, 32), out_wide, dw, dbias_thin,
-                             partials, partials_bytes, batch, nsplit_of(precision), (cudaStream_t)stream);
+  (void)backend; (void)precision;
   return thin_bwd_fused(make_operand(wide, 32), make_operand(thin, 3), w, make_epilogue(epi, 32), out_wide, dw, dbias_thin,
                         partials, partials_bytes, batch, (cudaStream_t)stream, 0);
 }

@@ -17,14 +17,6 @@ int thin_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias
 size_t thin_wgrad_workspace_bytes(int batch);
 int thin_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
                    float* dbias, void* partials, size_t bytes, int batch, cudaStream_t st, int phase);
-int thin_tc_gather_fwd(const Operand& thin, const float* w, const Epilogue& epi, float* out, int batch, int nsplit, cudaStream_t st);
-int thin_tc_wgrad(const Operand& wide, const Operand& thin, float* dw, float* dbias, void* partials, size_t bytes, int batch,
-                  int nsplit, cudaStream_t st);
-int thin_tc_bwd_fused(const Operand& wide, const Operand& thin, const float* w, const Epilogue& epi, float* out_wide, float* dw,
-                      float* dbias, void* partials, size_t bytes, int batch, int nsplit, cudaStream_t st);
-int thin_tc_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* bias, float* x_hat, const float* x,
-                                double* sse, int batch, int nsplit, cudaStream_t st);
-size_t thin_tc_wgrad_workspace_bytes(int batch);
 int bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float* rmean, float* rvar,
                 float* bnc, int C, int training, cudaStream_t st);
 int bn_bwd_reduce(const double* stats, int64_t count, const float* gamma, float* bnc, float* dgamma, float* dbeta, int C,
@@ -276,7 +268,6 @@ static size_t carve(ae_engine* e, char* base) {
   upd((size_t)colgemm_default_split((int)B, 128, L) * 128 * L * 4);
   upd((size_t)e->fc_split * B * L * 4);
   upd(thin_wgrad_workspace_bytes((int)B));
-  upd(thin_tc_wgrad_workspace_bytes((int)B));
   upd(head_fused_workspace_floats((int)B, L, NC) * 4);
   e->partial_bytes = pb;
   e->partial = (float*)take(pb);
@@ -548,8 +539,8 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
     Epilogue ep = training ? bias_stats_epilogue(P.P(1), P.bn[0].stats_f, 32)
                            : fused_eval ? bnrelu_split_epilogue(P.P(1), P.bn[0].bnc, 32, e->nsplit) : store_epilogue(P.P(1));
     ep.C = 32;
-    // fp32 CUDA cores: the tcgen05 variant (thin_tc_gather_fwd, 27 vs 37 us) puts the 2-term-split error into the very first
-    // layer, which BatchNorm's backward then amplifies; not worth 1 % of the step
+    // fp32 CUDA cores: a tcgen05 variant was measured in round 1: no faster once the CUDA-core kernel was
+    // register-tiled, and it puts the 2-term-split error into the very first layer, which BatchNorm's backward amplifies
     AE_TRY(thin_gather_fwd(raw_operand(x), P.P(0), ep, fused_eval ? (float*)e->ae_pl[0] : e->y[0], batch, st));
   }
   for (int i = 0; i < 3; ++i) {
@@ -703,7 +694,6 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
   }
   if (!fused_eval) AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
   float* xo = x_hat ? x_hat : e->xhat;
-  // (thin_tc_scatter_sigmoid_fwd: same speed as the fp32 CUDA-core kernel, which is the more exact one)
   AE_TRY(thin_scatter_sigmoid_fwd(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), P.P(14), P.P(15), xo, x_target, e->sse, batch, st));
   if (x_hat && training) AE_CUDA(cudaMemcpyAsync(e->xhat, x_hat, (size_t)batch * 12288 * 4, cudaMemcpyDeviceToDevice, st));
   e->last_z_dec = z;
@@ -724,7 +714,6 @@ static int decoder_backward_impl(ae_engine_t* e, const Operand& thin_up, int bat
   Part& P = e->part[AE_PART_DEC];
   const int L = e->L;
   // convT4 (32 -> 3)
-  // (thin_tc_bwd_fused: same speed as the fp32 CUDA-core kernel)
   {
     const Operand wide = bnrelu_operand(e->t[2], P.bn[2].bnc, 32);
     const Epilogue ep = relubwd_epilogue(e->t[2], P.bn[2].bnc, P.bn[2].stats_b, 32);

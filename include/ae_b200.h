@@ -142,8 +142,9 @@ int ae_conv2d_s2_wgrad(const ae_conv_geom_t* g, const ae_operand_t* big, const a
  * Thin (3-channel) layers: Conv2d(3,32) NB:504 and ConvTranspose2d(32,3)+Sigmoid NB:628-629.
  * thin = [B,3,64,64] NCHW fp32 (the reference's image layout), wide = [B,32,32,32] NHWC.
  * ---------------------------------------------------------------------------------------- */
-/* backend AE_BACKEND_TC: the threads only build bf16 (hi/lo) operand tiles, tcgen05 does the arithmetic (thin_tc.cu);
- * AE_BACKEND_SIMT: fp32 CUDA cores (thin.cu).  `precision` as for the GEMM kernels. */
+/* K = 27 / N = 3 do not fill a tensor-core tile: both backends run the fp32 CUDA-core kernels of thin.cu (a tcgen05 variant
+ * was measured in round 1 and was no faster).  `precision` only selects the number of bf16 planes an
+ * AE_EPI_BNRELU_SPLIT epilogue writes. */
 int ae_thin_gather_fwd(const ae_operand_t* thin, const float* w /*[32,3,3,3]*/, const ae_epilogue_t* epi,
                        float* out_wide, int batch, int precision, int backend, ae_stream_t stream);
 /* x_hat = sigmoid(convT(wide) + bias); if x != NULL also accumulates sum((x_hat-x)^2) into *sse (fp64) */

@@ -18,7 +18,12 @@ TOL = {"fp32": 1e-4, "bf16": 1e-2}
 # the fp64 oracle.  BatchNorm's backward removes the batch-mean and the xhat-correlated part of the incoming gradient,
 # which amplifies the relative error of whatever arithmetic produced it by |dz|/|dy| (10-100x in this network):
 # fp32 CUDA cores (1e-7) -> ~1e-5, 2-term bf16 split on tcgen05 (1e-5) -> ~3e-3, plain bf16 (4e-3) -> ~0.2.
-GRAD_TOL = {("simt", "fp32"): 1e-3, ("tc", "fp32"): 1e-2, ("tc", "bf16"): 0.35}
+GRAD_TOL = {("simt", "fp32"): 1e-3, ("tc", "fp32"): 1e-2, ("tc", "bf16"): 0.2}      # measured: 9e-4 / 3e-3 / 0.15
+# max-norm (max|g - g_ref| / max|g_ref|) and direction (cosine) of every parameter's gradient; a single entry may sit on the
+# other side of a ReLU in any other arithmetic, so the max-norm is looser than the L2 norm -- but never vacuous
+# measured on a B200 (batches 33 / 256): max-norm 1.6e-2 / 1.6e-2 / 0.22, cosine 1.00000 / 0.99999 / 0.9896
+GRAD_MAX_TOL = {("simt", "fp32"): 3e-2, ("tc", "fp32"): 5e-2, ("tc", "bf16"): 0.35}
+GRAD_COS = {("simt", "fp32"): 0.9999, ("tc", "fp32"): 0.9995, ("tc", "bf16"): 0.98}
 
 
 def dev():
