@@ -469,7 +469,11 @@ def dp_gradient_check(dev, world, rank, comm, model, opt, stepper, xs_d, ys_d):
     stepper.load(x, y)
     stepper.run()
     torch.cuda.synchronize()
-    g_nccl = flat.grad.clone() / world
+    fused = getattr(flat, "_dp_flags", None) is not None      # reduce-scatter + Adam + all-gather in one kernel over peer memory
+    g_nccl = flat.grad.clone()
+    if fused:                                                 # the gradient buffer then still holds this rank's OWN gradient
+        dist.all_reduce(g_nccl)
+    g_nccl /= world
     p1 = flat.data.clone()
     gx = [torch.empty_like(x) for _ in range(world)]
     gy = [torch.empty_like(y) for _ in range(world)]
@@ -485,6 +489,14 @@ def dp_gradient_check(dev, world, rank, comm, model, opt, stepper, xs_d, ys_d):
             acc += ref.engine().flat.grad.double()
         g_ref = (acc / world).float()
         grad_rel = float((g_nccl - g_ref).norm() / g_ref.norm())
+        # run-to-run noise floor of the single-GPU path itself (fp32 shared-memory atomics in the BatchNorm statistics
+        # arrive in a different order every launch; BatchNorm's backward amplifies that): shard 0 twice
+        twice = []
+        for _ in range(2):
+            ref.load_state_dict(state0)
+            ref.train_step_grads(gx[0], gy[0], ALPHA)
+            twice.append(ref.engine().flat.grad.double().clone())
+        noise = float((twice[0] - twice[1]).norm() / twice[0].norm())
         group = opt.param_groups[0]
         b1, b2 = group["betas"]
         t = step0 + 1
@@ -492,11 +504,16 @@ def dp_gradient_check(dev, world, rank, comm, model, opt, stepper, xs_d, ys_d):
         v = v0 * b2 + g_ref * g_ref * (1 - b2)
         denom = v.sqrt() / (1 - b2 ** t) ** 0.5 + group["eps"]
         p_pred = p0 - (group["lr"] / (1 - b1 ** t)) * (m / denom)
-        upd_rel = float((p1 - p_pred).norm() / (p_pred - p0).norm())
+        # fused path: every rank keeps Adam's moments of its own 1/world shard only -- rank 0 can predict its shard
+        # (the first 864 elements, conv1.weight, are an exchange round of their own: rank 0's shard of the rest follows them)
+        own = slice(864, 864 + (((flat.len - 864) // 4 + world - 1) // world) * 4) if fused else slice(0, flat.len)
+        upd_rel = float((p1[own] - p_pred[own]).norm() / (p_pred[own] - p0[own]).norm())
         # the same prediction with the SUM instead of the mean: how far off a missing 1/world would be
         ms_, vs_ = m0 + (g_ref * world - m0) * (1 - b1), v0 * b2 + (g_ref * world) ** 2 * (1 - b2)
         p_bad = p0 - (group["lr"] / (1 - b1 ** t)) * (ms_ / (vs_.sqrt() / (1 - b2 ** t) ** 0.5 + group["eps"]))
-        out = {"grad_rel": grad_rel, "update_rel": upd_rel, "update_rel_if_scale_were_missing": float((p1 - p_bad).norm() / (p_bad - p0).norm()),
+        out = {"path": "fused reduce-scatter + Adam + all-gather over NVLink peer memory (k_dp_adam)" if fused else "NCCL allreduce + Adam",
+               "grad_rel": grad_rel, "grad_rel_run_to_run_single_gpu": noise, "update_rel": upd_rel,
+               "update_rel_if_scale_were_missing": float((p1[own] - p_bad[own]).norm() / (p_bad[own] - p0[own]).norm()),
                "world": world, "adam_step": t, "batch_per_gpu": int(B),
                "what": "rel-L2 of NCCL gradient/world (and of the parameters after the captured step) against per-shard single-GPU gradients averaged on rank 0"}
     dist.barrier()

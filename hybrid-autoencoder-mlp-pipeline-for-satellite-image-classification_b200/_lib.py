@@ -17,6 +17,7 @@ EPI_STORE, EPI_BIAS_STATS, EPI_RELUBWD_STATS, EPI_BNRELU_SPLIT = 0, 1, 2, 3
 PART_ENC, PART_DEC, PART_HEAD = 0, 1, 2
 BNC_ROWS = 8
 DP_UNIQUE_ID_BYTES = 128
+DP_IPC_HANDLE_BYTES, DP_FLAG_BYTES = 64, 128
 
 c_void_p, c_int, c_int64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -110,6 +111,9 @@ _SIGS = {
     "ae_dp_init": (c_int, [c_void_p, c_int, c_int, P(c_void_p)]),
     "ae_dp_allreduce": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ae_dp_world": (c_int, [c_void_p]),
+    "ae_dp_ipc_export": (c_int, [c_void_p, c_void_p, P(c_int64)]),
+    "ae_dp_peers_attach": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
+    "ae_dp_max_ctas": (c_int, [c_void_p]),
     "ae_dp_destroy": (None, [c_void_p]),
 }
 

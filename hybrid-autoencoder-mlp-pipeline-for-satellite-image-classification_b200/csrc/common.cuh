@@ -229,6 +229,15 @@ int pack_conv_simt(const float* w, int Cs, int Cb, float* fwd, float* dgrad, cud
 int pack_linear(const float* w, int N, int K, int permC, int permHW, int kind, float* dst, cudaStream_t st);
 int permute_vector(const float* src, int n, int permC, int permHW, float* dst, cudaStream_t st);
 
+// fused data-parallel exchange over peer memory (dp.cu)
+struct DpAttachment;
+}  // namespace ae
+struct ae_dp_comm;
+namespace ae {
+const DpAttachment* dp_find_attachment(const ae_dp_comm* c, const float* flat_params, const float* flat_grads, int64_t flat_len);
+int dp_adam_fused(const ae_dp_comm* c, const DpAttachment* at, float* m, float* v, int64_t lo, int64_t n, float lr, float b1, float b2,
+                  float eps, float wd, int* step_dev, int bump, cudaStream_t st);
+
 // tcgen05 + TMA path (tma_gemm.cu)
 size_t tma_packed_bytes(int Cs, int Cb, int nsplit);
 int tma_pack_conv(const float* w, int Cs, int Cb, int nsplit, void* fwd, void* dgrad, cudaStream_t st);
@@ -240,6 +249,7 @@ bool tma_rowgemm_supported(const RowGemm& p);
 bool rowgemm2_supported(const RowGemm& p);   // shape + epilogue
 bool rowgemm2_preferred(const RowGemm& p);   // ... and measured to be the faster generation for this problem size
 int tma_rowgemm2(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);
+void rowgemm2_set_sm_reserve(int sms);       // SMs its one-CTA-per-SM grids leave to concurrently running collectives
 bool tma_wgrad_supported(const Geom& g);
 int tma_wgrad_slices(const Geom& g);
 size_t tma_wgrad_partial_bytes(const Geom& g);

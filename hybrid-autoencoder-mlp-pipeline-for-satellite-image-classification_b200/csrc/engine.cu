@@ -118,6 +118,7 @@ struct ae_engine {
   size_t partial_side_bytes = 0;
   // data-parallel step being captured: gradient exchange interleaved with the backward pass
   ae_dp_comm_t* step_comm = nullptr;
+  bool dp_single = false;             // data-parallel variant: no exchange inside the backward pass, one allreduce of the flat buffer after it
   bool defer_conv1_wgrad = false;     // the captured step runs conv1's weight gradient beside Adam + re-pack of everything else
   bool stats_cleared = false;         // the fused step zeroed every statistic accumulator in one memset: the parts skip theirs
   // pointers remembered between forward and backward
@@ -855,7 +856,7 @@ int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int bat
   up.src = x; up.src2 = e->xhat; up.bnc = nullptr; up.scalar = (float)(2.0 * (double)alpha / numel);
   up.mode = AE_OP_SIGMOID_BWD; up.C = 1;
   AE_TRY(decoder_backward_impl(e, up, batch, e->dz_tot, e->dz_head, st));
-  if (e->step_comm) {
+  if (e->step_comm && !e->dp_single) {
     // data parallel: the decoder's and the head's gradients are complete -- exchange them beside the encoder backward
     AE_TRY(ensure_side(e));
     AE_CUDA(cudaEventRecord(e->ev_fork2, st));
@@ -865,7 +866,7 @@ int ae_train_step(ae_engine_t* e, const float* x, const int64_t* labels, int bat
     AE_TRY(ae_dp_allreduce(e->step_comm, H.grads, H.flat_len, e->side2));
   }
   AE_TRY(ae_encoder_backward(e, e->dz_tot, batch, stream));
-  if (e->step_comm) {
+  if (e->step_comm && !e->dp_single) {
     Part& E = e->part[AE_PART_ENC];
     if (e->defer_conv1_wgrad) {
       // captured step: every encoder gradient except conv1.weight (still to be computed) is final -- exchange them on the
@@ -918,15 +919,26 @@ int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels,
   // buffer, every one of them on a side branch beside compute (decoder + head beside the encoder backward, the encoder
   // beside conv1's weight gradient, conv1.weight beside Adam + re-pack of everything else)
   e->step_comm = comm;
+  rowgemm2_set_sm_reserve(comm ? ae_dp_max_ctas(comm) : 0);
   // tcgen05 path: conv1's weight gradient (the last 40 us of the backward pass, and the only gradient still missing) runs
   // beside Adam + weight re-pack of every other parameter (single GPU) / beside the encoder's gradient exchange (data
   // parallel); its own 864 weights are updated after the join.
   const int64_t c1 = 864;   // conv1.weight = the first tensor of the encoder part
   const bool split_tail = !e->simt && e->part[AE_PART_ENC].params == flat_params && flat_len > c1;
   e->defer_conv1_wgrad = split_tail;
+  const char* tail_env = getenv("AE_B200_DP_TAIL");
+  const int dp_tail = tail_env ? atoi(tail_env) : 0;
+  // peers attached for exactly these flat buffers (ae_dp_peers_attach): reduce-scatter + Adam + all-gather as ONE kernel over
+  // NVLink peer memory instead of NCCL allreduces + Adam (AE_B200_DP_FUSED=0 keeps the NCCL form)
+  const char* fused_env = getenv("AE_B200_DP_FUSED");
+  const DpAttachment* peers = comm && split_tail && !(fused_env && atoi(fused_env) == 0)
+                                  ? dp_find_attachment(comm, flat_params, flat_grads, flat_len) : nullptr;
+  e->dp_single = comm != nullptr && split_tail && (dp_tail == 2 || peers != nullptr);
   int rc = ae_train_step(e, x, labels, batch, alpha, loss_out, stream);
   e->step_comm = nullptr;
   e->defer_conv1_wgrad = false;
+  e->dp_single = false;
+  rowgemm2_set_sm_reserve(0);
   float gscale = 1.f;
   if (rc == 0 && comm) gscale = 1.f / (float)ae_dp_world(comm);
   auto adam_range = [&](int64_t lo, int64_t n, int bump) {
@@ -940,7 +952,37 @@ int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels,
     }
     return 0;
   };
-  if (rc == 0 && split_tail && comm) {
+  if (rc == 0 && peers) {
+    // as on one GPU: conv1's weight gradient beside the exchange + update + re-pack of every other parameter; its own 864
+    // weights get a (tiny) exchange round of their own after the join
+    auto fused = [&](int64_t lo, int64_t n, int bump) {
+      return dp_adam_fused(comm, peers, adam_m, adam_v, lo, n, adam->lr, adam->beta1, adam->beta2, adam->eps, adam->weight_decay,
+                           step_dev, bump, st);
+    };
+    rc = fork_side(e, st);
+    if (rc == 0) rc = conv1_wgrad(e, batch, e->side);
+    if (rc == 0) rc = fused(c1, flat_len - c1, 0);
+    if (rc == 0) rc = pack_all_parts(e, st);
+    if (rc == 0) rc = join_side(e, st);
+    if (rc == 0) rc = fused(0, c1, 1);
+  } else if (rc == 0 && split_tail && comm && dp_tail == 2) {
+    // variant: ONE allreduce of the whole flat gradient buffer after the backward pass (SURVEY 8e as written)
+    rc = conv1_wgrad(e, batch, st);
+    if (rc == 0) rc = ae_dp_allreduce(comm, flat_grads, flat_len, st);
+    if (rc == 0) rc = adam_range(0, flat_len, 1);
+    if (rc == 0) rc = pack_all_parts(e, st);
+  } else if (rc == 0 && split_tail && comm && dp_tail == 1) {
+    // variant: conv1's weight gradient on the side branch, beside the encoder's gradient exchange (side2) and then beside
+    // Adam + re-pack of every other parameter; the exchange of its own 864 gradients is left exposed at the end
+    rc = fork_side(e, st);
+    if (rc == 0) rc = conv1_wgrad(e, batch, e->side);
+    if (rc == 0) rc = link(e->ev_join2, e->side2, st);       // decoder, head, encoder (without conv1.weight) are exchanged
+    if (rc == 0) rc = adam_range(c1, flat_len - c1, 0);
+    if (rc == 0) rc = pack_all_parts(e, st);
+    if (rc == 0) rc = join_side(e, st);
+    if (rc == 0) rc = ae_dp_allreduce(comm, flat_grads, c1, st);
+    if (rc == 0) rc = adam_range(0, c1, 1);
+  } else if (rc == 0 && split_tail && comm) {
     rc = conv1_wgrad(e, batch, st);
     // every exchange issued so far (decoder, head, encoder without conv1.weight) is complete before Adam reads it
     if (rc == 0) rc = link(e->ev_join2, e->side2, st);

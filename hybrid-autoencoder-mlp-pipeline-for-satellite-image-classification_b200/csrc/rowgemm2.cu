@@ -484,6 +484,10 @@ extern "C" int ae_debug_set_trace2(unsigned long long* buf) {
 }
 #endif
 
+// SMs left to concurrently running collectives (set by the engine while it captures a data-parallel step)
+static int g_sm_reserve = 0;
+void rowgemm2_set_sm_reserve(int sms) { g_sm_reserve = sms > 0 ? sms : 0; }
+
 bool rowgemm2_supported(const RowGemm& p) {
   if (!tma_rowgemm_supported(p)) return false;
   if (p.epi.mode != AE_EPI_STORE && p.epi.mode != AE_EPI_BIAS_STATS && p.epi.mode != AE_EPI_RELUBWD_STATS) return false;
@@ -538,7 +542,8 @@ static int launch_row2(TmaRow2& q, cudaStream_t st) {
     if (dev < 16) attr_set[dev] = smem;
   }
   const int tiles = ((q.M + TILE_M - 1) / TILE_M) * tiles_n;
-  const int ctas = tiles < sms ? tiles : sms;
+  const int avail = sms - g_sm_reserve > 16 ? sms - g_sm_reserve : sms;      // one CTA per SM: a busy SM would cost a second wave
+  const int ctas = tiles < avail ? tiles : avail;
   k_rowgemm2<FAMILY, WT, KC, NSPLIT, NSUB><<<ctas, R2_THREADS, smem, st>>>(q);
   AE_LAUNCH_CHECK();
   return 0;

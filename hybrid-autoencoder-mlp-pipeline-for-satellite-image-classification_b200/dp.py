@@ -50,6 +50,44 @@ def init_communicator() -> Communicator:
     return comm
 
 
+def attach_peers(comm: Communicator, model) -> bool:
+    """Give the library peer-mapped views of every rank's flat parameter / gradient buffers of `model` (CUDA IPC, all ranks on
+    one box): a TrainStep captured afterwards with `comm` runs reduce-scatter + Adam + all-gather as ONE kernel over NVLink
+    instead of NCCL allreduces followed by Adam.  Adam's moments are then maintained for the own 1/world shard only.
+    Collective: every rank must call it.  Returns False (and changes nothing) when AE_B200_DP_FUSED=0."""
+    import os
+    if os.environ.get("AE_B200_DP_FUSED", "1") == "0" or comm.world > 8:
+        return False
+    lib = _lib.load()
+    eng = model.engine()
+    flat = eng.flat
+    if getattr(flat, "_dp_flags", None) is not None and flat._dp_flags[0] is comm:
+        return True
+    dev = flat.data.device
+    flags = torch.zeros(_lib.DP_FLAG_BYTES // 4, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)
+    mine = []
+    for t in (flat.data, flat.grad, flags):
+        h = (C.c_uint8 * _lib.DP_IPC_HANDLE_BYTES)()
+        off = C.c_int64()
+        check(lib.ae_dp_ipc_export(C.c_void_p(t.data_ptr()), h, C.byref(off)))
+        mine.append((bytes(h), int(off.value)))
+    everyone = [None] * comm.world
+    dist.all_gather_object(everyone, mine)
+    handles = (C.c_uint8 * (comm.world * 3 * _lib.DP_IPC_HANDLE_BYTES))()
+    offsets = (C.c_int64 * (comm.world * 3))()
+    for r, bufs in enumerate(everyone):
+        for b, (h, off) in enumerate(bufs):
+            base = (r * 3 + b) * _lib.DP_IPC_HANDLE_BYTES
+            handles[base:base + _lib.DP_IPC_HANDLE_BYTES] = list(h)
+            offsets[r * 3 + b] = off
+    check(lib.ae_dp_peers_attach(comm.handle, handles, offsets, C.c_void_p(flat.data.data_ptr()), C.c_void_p(flat.grad.data_ptr()),
+                                 C.c_void_p(flags.data_ptr()), flat.len))
+    flat._dp_flags = (comm, flags)       # keeps the flag block alive as long as the flat buffers
+    dist.barrier()                       # every rank has mapped (and zeroed) everything before anyone's first step
+    return True
+
+
 def shard_bounds(total: int, rank: int, world: int):
     """Contiguous batch shard [lo, hi) of `rank`: sizes differ by at most one, all shards non-empty when total >= world."""
     base, rem = divmod(total, world)

@@ -24,6 +24,9 @@ class TrainStep:
         self.device = dev
         eng = model.engine()
         eng.prepare(dev, batch)
+        if comm is not None:
+            from . import dp
+            dp.attach_peers(comm, model)         # collective; no-op when already attached or AE_B200_DP_FUSED=0
         self.x = torch.zeros(batch, 3, 64, 64, dtype=torch.float32, device=dev)
         self.y = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.loss = torch.zeros(4, dtype=torch.float32, device=dev)

@@ -331,7 +331,20 @@ void ae_step_graph_destroy(ae_step_graph_t* g);
 int ae_dp_get_unique_id(uint8_t* id_host /*[AE_DP_UNIQUE_ID_BYTES]*/);
 int ae_dp_init(const uint8_t* id_host, int rank, int world, ae_dp_comm_t** out);
 int ae_dp_allreduce(ae_dp_comm_t* c, float* buf, int64_t n, ae_stream_t stream);
+/* Fused exchange over NVLink peer memory (one process per GPU of ONE box): every rank exports the allocations that hold its
+ * flat parameter buffer, flat gradient buffer and a zeroed flag block of AE_DP_FLAG_BYTES, the host all-gathers the handles
+ * (torch.distributed) and attaches them.  A step captured with this communicator for exactly these flat buffers then replaces
+ * "allreduce + Adam" by ONE kernel: reduce-scatter out of the peers' gradient buffers, Adam on the own 1/world shard (only
+ * that shard of the moments is maintained), all-gather of the new parameters into every rank's buffer. */
+#define AE_DP_IPC_HANDLE_BYTES 64
+#define AE_DP_FLAG_BYTES 128
+int ae_dp_ipc_export(const void* dev_ptr, uint8_t* handle /*[AE_DP_IPC_HANDLE_BYTES]*/, int64_t* offset);
+int ae_dp_peers_attach(ae_dp_comm_t* c, const uint8_t* handles /*[world][3][AE_DP_IPC_HANDLE_BYTES]: params, grads, flags*/,
+                       const int64_t* offsets /*[world][3]*/, float* own_params, float* own_grads, void* own_flags,
+                       int64_t flat_len);
 int ae_dp_world(const ae_dp_comm_t* c);
+/* upper bound of the SMs one collective of this communicator occupies (ncclConfig_t.maxCTAs; AE_B200_NCCL_MAX_CTAS) */
+int ae_dp_max_ctas(const ae_dp_comm_t* c);
 void ae_dp_destroy(ae_dp_comm_t* c);
 
 #ifdef __cplusplus
