@@ -173,6 +173,46 @@ __device__ __forceinline__ float4 load_operand4(const Operand& op, size_t off, i
   return v;
 }
 
+// One BatchNorm coefficient job (what k_bn_finalize / k_bn_bwd_reduce do as launches), run by `nthreads` threads of ONE
+// CTA after the statistics are complete.  The statistics were accumulated by other SMs: they are read past L1.
+__device__ __forceinline__ void bn_job_run(const BnJob& job, int tid, int nthreads) {
+  const int C = job.C;
+  for (int c = tid; c < C; c += nthreads) {
+    if (job.kind == BN_JOB_FINALIZE) {
+      double mean, var;
+      if (job.training) {
+        mean = __ldcg(job.stats + c) / job.count;
+        var = __ldcg(job.stats + C + c) / job.count - mean * mean;
+        if (var < 0.0) var = 0.0;
+      } else {
+        mean = (double)job.rmean[c];
+        var = (double)job.rvar[c];
+      }
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      const float scale = job.gamma[c] * rstd;
+      const float shift = job.beta[c] - (float)mean * scale;
+      if (c == 0 && job.training && job.nbt) *job.nbt += 1;
+      if (job.training && job.rmean) {
+        const double unb = job.count > 1.0 ? var * job.count / (job.count - 1.0) : var;
+        job.rmean[c] = (float)(0.9 * (double)job.rmean[c] + 0.1 * mean);
+        job.rvar[c] = (float)(0.9 * (double)job.rvar[c] + 0.1 * unb);
+      }
+      job.bnc[AE_BNC_SCALE * C + c] = scale; job.bnc[AE_BNC_SHIFT * C + c] = shift;
+      job.bnc[AE_BNC_MEAN * C + c] = (float)mean; job.bnc[AE_BNC_RSTD * C + c] = rstd;
+    } else if (job.kind == BN_JOB_BWD) {
+      const double s1 = __ldcg(job.stats + c), s2 = __ldcg(job.stats + C + c);
+      const double rstd = (double)job.bnc[AE_BNC_RSTD * C + c];
+      const double a = (double)job.gamma[c] * rstd;
+      job.bnc[AE_BNC_A * C + c] = (float)a;
+      job.bnc[AE_BNC_B * C + c] = (float)(-a * rstd * s2 / job.count);
+      job.bnc[AE_BNC_C * C + c] = (float)(-a * s1 / job.count);
+      if (job.dgamma) job.dgamma[c] = (float)s2;
+      if (job.dbeta) job.dbeta[c] = (float)s1;
+      if (job.dzero) job.dzero[c] = 0.f;
+    }
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -199,6 +239,10 @@ struct RowGemm {
   float* out;
   int splitK;        // >1: partial[s][M][N] written instead of out (no bias / stats), DENSE/FPROP only
   float* partial;
+  // tcgen05 path: BatchNorm coefficient job of the statistics this launch accumulates, run by the LAST CTA to finish
+  // (a self-resetting counter in the caller's memory) instead of a k_bn_finalize / k_bn_bwd_reduce launch behind it
+  const BnJob* tail_job;
+  unsigned int* tail_counter;
 };
 int simt_rowgemm(const RowGemm& p, cudaStream_t st);
 

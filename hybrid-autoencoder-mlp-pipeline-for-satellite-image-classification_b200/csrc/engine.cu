@@ -275,7 +275,7 @@ static size_t carve(ae_engine* e, char* base) {
   e->head_partial = (float*)take(head_fused_workspace_floats((int)B, L, NC) * 4);
   e->partial_side_bytes = (size_t)colgemm_default_split((int)B, 4096, L) * 4096 * L * 4;
   e->partial_side = (float*)take(e->partial_side_bytes);
-  e->head_counter = (unsigned int*)take(256);
+  e->head_counter = (unsigned int*)take(256);      // [0..31]: head; [40]: last-CTA counter of a row GEMM's BatchNorm tail job
   return off + 256;
 }
 
@@ -564,10 +564,14 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
       continue;
     }
     const BnJob job = bn_fwd_job(P, i, batch, training);      // BatchNorm of this layer's input, finalised in the split
+    // the last convolution's own BatchNorm has no split behind it (the dense layer applies it while loading): its
+    // coefficient job rides on this launch (last CTA out) instead of a launch of its own
+    const BnJob last = bn_fwd_job(P, 3, batch, training);
+    if (i == 2 && !e->simt) { r.tail_job = &last; r.tail_counter = e->head_counter + 40; }
     AE_TRY(run_rowgemm(e, r, bnrelu_operand(e->y[i], bin.bnc, bin.C), e->ae_pl[i], true,
                        (int64_t)batch * bin.count_per_image * bin.C, m.pk_fwd, &job, st));
   }
-  if (!fused_eval) AE_TRY(run_bn_job(bn_fwd_job(P, 3, batch, training), st));
+  if (!fused_eval && e->simt) AE_TRY(run_bn_job(bn_fwd_job(P, 3, batch, training), st));
   {  // Flatten + Linear(4096, L): split-K partials, fixed-order reduce (+bias)
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = e->L; r.K = 4096;
@@ -635,10 +639,13 @@ int ae_encoder_backward(ae_engine_t* e, const float* dz, int batch, ae_stream_t 
     r.Bp = (const float*)m.pk_dgrad;
     r.epi = relubwd_epilogue(e->y[i], bin.bnc, bin.stats_b, bin.C);
     r.out = e->dzy[i]; r.splitK = 1;
+    // the first layer's BatchNorm backward job (nothing is split behind it: conv1's weight gradient applies it while loading)
+    const BnJob first = bn_bwd_job(P, 0, batch, P.G(1));
+    if (i == 0 && !e->simt) { r.tail_job = &first; r.tail_counter = e->head_counter + 40; }
     AE_TRY(run_rowgemm(e, r, dy_small, dyp, false, 0, m.pk_dgrad, nullptr, st));
     if (!e->simt) AE_TRY(join_side(e, st));
   }
-  AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch, P.G(1)), st));
+  if (e->simt) AE_TRY(run_bn_job(bn_bwd_job(P, 0, batch, P.G(1)), st));
   if (!e->defer_conv1_wgrad) AE_TRY(conv1_wgrad(e, batch, st));
   return 0;
 }
@@ -690,10 +697,13 @@ static int decoder_forward_impl(ae_engine_t* e, const float* z, int batch, int t
     }
     BnJob job{};
     if (i > 0) job = bn_fwd_job(P, i - 1, batch, training);
+    // the last 32..256-channel layer's BatchNorm is applied by the 3-channel scatter kernel while loading: its job rides here
+    const BnJob last = bn_fwd_job(P, 2, batch, training);
+    if (i == 2 && !e->simt) { r.tail_job = &last; r.tail_counter = e->head_counter + 40; }
     AE_TRY(run_rowgemm(e, r, a, i == 0 ? e->h_pl : e->ad_pl[i - 1], i > 0 || e->simt, (int64_t)r.M * m.g.Cs, m.pk_dgrad,
                        i > 0 ? &job : nullptr, st));
   }
-  if (!fused_eval) AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
+  if (!fused_eval && e->simt) AE_TRY(run_bn_job(bn_fwd_job(P, 2, batch, training), st));
   float* xo = x_hat ? x_hat : e->xhat;
   AE_TRY(thin_scatter_sigmoid_fwd(bnrelu_operand(e->t[2], P.bn[2].bnc, 32), P.P(14), P.P(15), xo, x_target, e->sse, batch, st));
   if (x_hat && training) AE_CUDA(cudaMemcpyAsync(e->xhat, x_hat, (size_t)batch * 12288 * 4, cudaMemcpyDeviceToDevice, st));

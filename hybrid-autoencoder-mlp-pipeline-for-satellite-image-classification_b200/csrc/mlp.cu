@@ -7,13 +7,15 @@
 // fixed order (deterministic).  The only global traffic is x, the row-local intermediates and the results.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace ae {
 
-static constexpr int H1 = 128, H2 = 64, CP = 16, CHUNK = 32, NT = 256, NCTA = 8;
+static constexpr int H1 = 128, H2 = 64, CP = 16, CHUNK = 32, NT = 256;   // cluster size: template parameter of k_mlp
 static constexpr int LD1 = H1 + 1, LD2 = H2 + 1, LD3 = CP + 1;
 static constexpr float BN_EPS_F = 1e-5f;
 
@@ -34,6 +36,10 @@ struct MlpArgs {
   float* h1; float* h2; float* d1; float* d2; float* dlog; uint8_t* keep; float* bnc;  // bnc: [2][4][128]
   int B, D, C, flags;
   unsigned long long seed;
+  // graph-replayable step (ae_mlp_train_step): the dropout seed of launch i is seed + seed_dev[0], and the launch advances
+  // seed_dev[0] and both BatchNorm layers' num_batches_tracked itself
+  unsigned long long* seed_dev;
+  int64_t* nbt;             // [2] or NULL
   float p;
   int64_t off[10];
 };
@@ -47,6 +53,7 @@ __device__ __forceinline__ unsigned hash_u32(unsigned long long seed, unsigned r
 }
 
 // Sum `n` per-CTA fp32 partials (S slots each) over the cluster in a fixed order -> tot[n] (double).
+template <int NCTA>
 __device__ void cluster_sum(cg::cluster_group& cl, float* part, int slots, int n, double* tot) {
   cl.sync();
   for (int i = threadIdx.x; i < n; i += NT) {
@@ -96,7 +103,10 @@ __device__ __forceinline__ void tile_linear(const float* __restrict__ inT, int K
   }
 }
 
-__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
+// NCTA = CTAs of the one cluster that owns the batch (launch attribute): 8 for large batches; small training batches
+// (the reference trains the MLP at batch 64, NB:3443) are bound by the cluster-wide exchanges, not by arithmetic.
+template <int NCTA>
+__global__ void __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
   extern __shared__ __align__(16) float sm[];
   cg::cluster_group cl = cg::this_cluster();
   const int tid = threadIdx.x;
@@ -132,6 +142,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
   const int rows_per = (B + NCTA - 1) / NCTA;
   const int r0 = min(B, (int)rank * rows_per), r1 = min(B, r0 + rows_per);
   const float keep_scale = 1.f / (1.f - a.p);
+  const unsigned long long seed = a.seed + (a.seed_dev ? a.seed_dev[0] : 0ull);
   float* c1 = coef;            // layer 1: scale, shift, mean, rstd, A, B, C  (rows of 128)
   float* c2 = coef + 7 * H1;   // layer 2
   __syncthreads();
@@ -157,7 +168,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
     }
     if (training) {
       // slots: 2 row groups x {sum, sumsq} x 128 -> view as 2 slots of n = 256
-      cluster_sum(cl, part, 2, 2 * H1, tot);
+      cluster_sum<NCTA>(cl, part, 2, 2 * H1, tot);
     } else {
       __syncthreads();
     }
@@ -196,7 +207,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
             if (training && a.p > 0.f) {
               unsigned char kp;
               if (a.keep_in) kp = a.keep_in[g];
-              else kp = (hash_u32(a.seed, c0 + r, k) * (1.0f / 4294967296.0f)) >= a.p ? 1 : 0;
+              else kp = (hash_u32(seed, c0 + r, k) * (1.0f / 4294967296.0f)) >= a.p ? 1 : 0;
               if (a.keep) a.keep[g] = kp;
               v = kp ? v * keep_scale : 0.f;
             }
@@ -211,7 +222,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
       part[(rg * 2 + 0) * H2 + j] = s1;
       part[(rg * 2 + 1) * H2 + j] = s2;
     }
-    if (training) cluster_sum(cl, part, 4, 2 * H2, tot);
+    if (training) cluster_sum<NCTA>(cl, part, 4, 2 * H2, tot);
     else __syncthreads();
     for (int j = tid; j < H2; j += NT) {
       float mean, var;
@@ -276,7 +287,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
         for (int o = 16; o > 0; o >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, o);
         if (tid == 0) { part[0] = lsum; part[1] = (float)ok; }
       }
-      cluster_sum(cl, part, 1, 2, tot);
+      cluster_sum<NCTA>(cl, part, 1, 2, tot);
       if (rank == 0 && tid == 0) {
         if (a.loss) a.loss[0] = (float)(tot[0] / B);
         if (a.correct) a.correct[0] = (int)(tot[1] + 0.5);
@@ -346,7 +357,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
         part[(rg * 2 + 0) * H2 + k] = s1;
         part[(rg * 2 + 1) * H2 + k] = s2;
       }
-      cluster_sum(cl, part, 4, 2 * H2, tot);
+      cluster_sum<NCTA>(cl, part, 4, 2 * H2, tot);
       for (int k = tid; k < H2; k += NT) {
         const double S1 = tot[k], S2 = tot[H2 + k];
         const double rstd = c2[3 * H1 + k];
@@ -436,7 +447,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
       }
       part[(jg * 2 + 0) * H1 + kk] = s1;
       part[(jg * 2 + 1) * H1 + kk] = s2;
-      cluster_sum(cl, part, 2, 2 * H1, tot);
+      cluster_sum<NCTA>(cl, part, 2, 2 * H1, tot);
       for (int k = tid; k < H1; k += NT) {
         const double S1 = tot[k], S2 = tot[H1 + k];
         const double rstd = c1[3 * H1 + k];
@@ -502,6 +513,13 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1) k_mlp(MlpA
     }
   }
   (void)misc;
+  if (a.seed_dev || a.nbt) {
+    cl.sync();                                 // every CTA has read the seed
+    if (rank == 0 && tid == 0) {
+      if (a.seed_dev) a.seed_dev[0] += 0x9E3779B97F4A7C15ull;
+      if (a.nbt && training) { a.nbt[0] += 1; a.nbt[1] += 1; }
+    }
+  }
 }
 
 
@@ -626,21 +644,44 @@ static size_t mlp_carve(int B, char* base, MlpWs* w) {
   return off + 256;
 }
 
+template <int NCTA>
+static int mlp_launch_n(MlpArgs& a, cudaStream_t st) {
+  const size_t smem = mlp_smem_bytes(a.D);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AE_CUDA(cudaFuncSetAttribute(k_mlp<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem_bytes(64)));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NCTA, 1, 1); cfg.blockDim = dim3(NT, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  AE_CUDA(cudaLaunchKernelEx(&cfg, k_mlp<NCTA>, a));
+  return 0;
+}
+
 static int mlp_launch(MlpArgs& a, cudaStream_t st) {
   AE_CHECK(a.D >= 4 && a.D <= 64 && a.D % 4 == 0, "mlp: input_dim=%d must be a multiple of 4 in [4,64]", a.D);
   AE_CHECK(a.C >= 2 && a.C <= 12, "mlp: num_classes=%d must be in [2,12]", a.C);
   AE_CHECK(a.B >= 1, "mlp: empty batch");
-  const size_t smem = mlp_smem_bytes(a.D);
-  static bool attr_set = false;
-  if (!attr_set) {
-    AE_CUDA(cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem_bytes(64)));
-    attr_set = true;
-  }
   mlp_layout(a.D, a.C, a.off, nullptr);
-  k_mlp<<<NCTA, NT, smem, st>>>(a);
-  AE_LAUNCH_CHECK();
-  return 0;
+  // cluster size by batch (AE_B200_MLP_CLUSTER overrides, for measurements).  Measured at the reference's batch 64, whole
+  // step replayed as a graph: 148 / 101 / 97 / 97 us with 1 / 2 / 4 / 8 CTAs -- one CTA is bound by arithmetic (256 threads),
+  // from 4 CTAs up by the cluster-wide exchanges.
+  int nc = a.B >= 48 ? 8 : a.B >= 24 ? 4 : a.B >= 12 ? 2 : 1;
+  if (const char* ev = getenv("AE_B200_MLP_CLUSTER")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8) nc = v; }
+  switch (nc) {
+    case 1: return mlp_launch_n<1>(a, st);
+    case 2: return mlp_launch_n<2>(a, st);
+    case 4: return mlp_launch_n<4>(a, st);
+    default: return mlp_launch_n<8>(a, st);
+  }
 }
+
+int adam_step_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                   float gscale, int* step_dev, cudaStream_t st);   // elementwise.cu
 
 }  // namespace ae
 
@@ -698,6 +739,33 @@ int ae_mlp_forward_eval(const float* params, const float* bn_running, const floa
   k_mlp_eval<<<grid, NT, smem, (cudaStream_t)stream>>>(params, bn_running, x, batch, input_dim, num_classes, lay, logits, argmax);
   AE_LAUNCH_CHECK();
   return 0;
+}
+
+// One whole MLP training step (NB:3476-3482: zero_grad, forward, CE, backward, Adam.step) as two launches with nothing baked
+// in that changes between steps: the dropout seed advances on the device, so the call can be captured in a CUDA graph and
+// replayed.  Also bumps both BatchNorm layers' num_batches_tracked (bn_steps, int64[2]).
+int ae_mlp_train_step(float* params, float* grads, float* bn_running, int64_t* bn_steps, const float* x, const int64_t* labels,
+                      uint64_t dropout_seed, uint64_t* seed_dev, float dropout_p, int batch, int input_dim, int num_classes,
+                      float* logits, float* loss, int* correct, void* workspace, size_t workspace_bytes,
+                      const ae_adam_config_t* adam, float* adam_m, float* adam_v, int* step_dev, ae_stream_t stream) {
+  AE_CHECK(params && grads && bn_running && x && labels && seed_dev && workspace && adam && adam_m && adam_v && step_dev,
+           "ae_mlp_train_step: null argument");
+  AE_CHECK(workspace_bytes >= mlp_carve(batch, nullptr, nullptr), "ae_mlp_train_step: workspace too small");
+  AE_CHECK(dropout_p >= 0.f && dropout_p < 1.f, "ae_mlp_train_step: dropout_p out of range");
+  MlpWs w;
+  mlp_carve(batch, (char*)workspace, &w);
+  MlpArgs a{};
+  a.params = params; a.grads = grads; a.running = bn_running; a.x = x; a.labels = labels; a.keep_in = nullptr;
+  a.dlogits_in = nullptr; a.logits = logits; a.loss = loss; a.correct = correct;
+  a.h1 = w.h1; a.h2 = w.h2; a.d1 = w.d1; a.d2 = w.d2; a.dlog = w.dlog; a.keep = w.keep; a.bnc = w.bnc;
+  a.B = batch; a.D = input_dim; a.C = num_classes; a.seed = dropout_seed; a.seed_dev = (unsigned long long*)seed_dev; a.nbt = bn_steps;
+  a.p = dropout_p;
+  a.flags = MLP_FWD | MLP_TRAIN | MLP_CE | MLP_BWD;
+  AE_TRY(mlp_launch(a, (cudaStream_t)stream));
+  int64_t off[10];
+  const int64_t n = mlp_layout(input_dim, num_classes, off, nullptr);
+  return adam_step_flat(params, grads, adam_m, adam_v, n, adam->lr, adam->beta1, adam->beta2, adam->eps, adam->weight_decay, 1.f,
+                        step_dev, (cudaStream_t)stream);
 }
 
 // backward of a preceding training-mode forward-only call (labels == NULL, same workspace), given d(loss)/d(logits)

@@ -60,6 +60,8 @@ struct alignas(64) TmaRow2 {
   int na, nw;               // ring slots
   int resident;             // the (single) n-tile's weight groups are loaded once and stay in the ring
   int bx, by, bn;           // pixel box of one 128-row tile
+  BnJob job;                // kind != BN_JOB_NONE: coefficient job of epi.stats, run by the last CTA to finish
+  unsigned int* job_counter;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -467,6 +469,22 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
         }
       }
     }
+    if (q.job.kind != BN_JOB_NONE) {
+      // last CTA out: every CTA's statistics are in (its fp64 atomics precede its count), derive the BatchNorm coefficients
+      __shared__ unsigned int s_last;
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+        const unsigned int done = atomicAdd(q.job_counter, 1u);
+        s_last = done == gridDim.x - 1 ? 1u : 0u;
+        if (s_last) *q.job_counter = 0u;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        bn_job_run(q.job, et, 256);
+      }
+    }
     if (et == 0) AE_TR2(9);
   }
   tc_fence_before();
@@ -558,6 +576,11 @@ int tma_rowgemm2(const RowGemm& p, const void* packed, int nsplit, cudaStream_t 
   memset(&q, 0, sizeof(q));
   q.wtiles = (const uint8_t*)packed;
   q.g = p.g; q.epi = p.epi; q.M = p.M; q.N = p.N;
+  if (p.tail_job) {
+    AE_CHECK(p.tail_counter != nullptr && p.tail_job->stats == p.epi.stats && p.tail_job->C <= 256,
+             "rowgemm2: the tail job must describe the statistics this launch accumulates");
+    q.job = *p.tail_job; q.job_counter = p.tail_counter;
+  }
   const Geom& g = p.g;
   pixel_box(g.Hs, g.Ws, TILE_M, &q.bx, &q.by, &q.bn);
   int bx32, by32, bn32;

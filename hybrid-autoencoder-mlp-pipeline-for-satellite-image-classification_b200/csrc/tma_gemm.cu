@@ -169,6 +169,8 @@ struct alignas(64) TmaRow {
   int cpt;                  // K chunks per tap (C / KC)
   int wchunks;              // K chunks per n-tile in the weight pack (all taps / all phases)
   int bx, by, bn;           // pixel box of one 128-row tile
+  BnJob job;                // kind != BN_JOB_NONE: coefficient job of epi.stats, run by the last CTA to finish
+  unsigned int* job_counter;
 };
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A tile is (phase, m-tile, n-tile) with
@@ -441,6 +443,22 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
         }
       }
     }
+    if (q.job.kind != BN_JOB_NONE) {
+      // last CTA out: every CTA's statistics are in (its fp64 atomics precede its count), derive the BatchNorm coefficients
+      __shared__ unsigned int s_last;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const unsigned int done = atomicAdd(q.job_counter, 1u);
+        s_last = done == gridDim.x - 1 ? 1u : 0u;
+        if (s_last) *q.job_counter = 0u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        bn_job_run(q.job, et, 128);
+      }
+    }
     if (et == 0) AE_TR(9);
   }
   tc_fence_before();
@@ -553,6 +571,11 @@ int tma_rowgemm(const RowGemm& p, const void* packed, int nsplit, cudaStream_t s
   memset(&q, 0, sizeof(q));
   q.wtiles = (const uint8_t*)packed;
   q.g = p.g; q.epi = p.epi; q.out = p.out; q.M = p.M; q.N = p.N;
+  if (p.tail_job) {
+    AE_CHECK(p.tail_counter != nullptr && p.tail_job->stats == p.epi.stats && p.tail_job->C <= 256,
+             "tma_rowgemm: the tail job must describe the statistics this launch accumulates");
+    q.job = *p.tail_job; q.job_counter = p.tail_counter;
+  }
   const Geom& g = p.g;
   pixel_box(g.Hs, g.Ws, TILE_M, &q.bx, &q.by, &q.bn);
   // 64-wide n-tiles keep the most CTAs busy at training batch sizes; with thousands of m-tiles (inference) a 128-wide tile

@@ -91,23 +91,37 @@ def fit_autoencoder(model, optimizer, train_loader: DeviceLoader, val_loader: De
 def train_epoch_mlp(clf, optimizer, X: torch.Tensor, y: torch.Tensor, batch_size: int = 64, shuffle: bool = True,
                     generator: Optional[torch.Generator] = None):
     """NB:3471-3489 over latents X [N,D] / labels y [N] that already live on the device (the reference wraps the CPU
-    copies in a TensorDataset, NB:3443).  Per batch: one fused kernel (forward + CE + backward) and one Adam launch; the
-    losses and correct counts stay in a device history and are read once.  Returns (train_loss, train_acc)."""
+    copies in a TensorDataset, NB:3443).  Per batch: ONE replay of a captured two-launch graph (cluster kernel: forward + CE
+    + backward; fused flat Adam) on a batch gathered into its input buffers; the losses and correct counts stay in a
+    device history and are read once.  Returns (train_loss, train_acc)."""
+    from .train import MLPTrainStep
     clf.train()
     n, dev = int(X.shape[0]), X.device
     order = torch.randperm(n, device=dev, generator=generator) if shuffle else torch.arange(n, device=dev)
     steps = (n + batch_size - 1) // batch_size
     hist = torch.zeros(steps, 2, dtype=torch.float32, device=dev)
     sizes = []
+    cache = clf.__dict__.setdefault("_train_steps", {})       # one captured step per (optimizer, batch size)
+    explicit_mask = clf._dropout_keep_override is not None     # test hook: the explicit-mask path is not graph-captured
     for k in range(steps):
         idx = order[k * batch_size:(k + 1) * batch_size]
-        xb, yb = X.index_select(0, idx), y.index_select(0, idx)
-        optimizer.zero_grad()
-        loss, correct, _ = clf.fused_step_grads(xb, yb)
-        optimizer.step()
+        b = int(idx.numel())
+        if explicit_mask:
+            xb, yb = X.index_select(0, idx), y.index_select(0, idx)
+            optimizer.zero_grad()
+            loss, correct, _ = clf.fused_step_grads(xb, yb)
+            optimizer.step()
+        else:
+            step = cache.get((id(optimizer), b))
+            if step is None or not step.valid():
+                step = cache[(id(optimizer), b)] = MLPTrainStep(clf, optimizer, b, dev)
+            torch.index_select(X, 0, idx, out=step.x)
+            torch.index_select(y, 0, idx, out=step.y)
+            step.run()
+            loss, correct = step.loss, step.correct
         hist[k, 0:1].copy_(loss, non_blocking=True)
         hist[k, 1:2].copy_(correct, non_blocking=True)        # int32 -> float32 (exact below 2^24)
-        sizes.append(int(idx.numel()))
+        sizes.append(b)
     h = hist.cpu()
     tot = sum(sizes)
     return sum(v * b for v, b in zip(h[:, 0].tolist(), sizes)) / tot, float(h[:, 1].sum()) / tot

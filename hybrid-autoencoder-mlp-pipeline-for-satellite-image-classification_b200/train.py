@@ -185,3 +185,62 @@ class TrainStep:
             self.close()
         except Exception:
             pass
+
+
+class MLPTrainStep:
+    """One MLP training step of the reference loop (NB:3476-3482: zero_grad, forward, cross-entropy, backward,
+    Adam.step) captured ONCE as a CUDA graph of two launches -- the cluster kernel (forward + BatchNorm1d + dropout + CE +
+    backward) and the fused flat Adam -- on fixed device buffers.  Nothing that changes between steps is baked in: the
+    dropout seed advances on the device.  `load` copies / gathers a batch into the buffers, `run` replays."""
+
+    def __init__(self, clf, optimizer: Adam, batch: int, device=None):
+        lib = _lib.load()
+        self.clf, self.opt, self.batch = clf, optimizer, int(batch)
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.device = dev
+        st = clf._state
+        st.prepare(dev, batch)
+        self._st, self._flat = st, st.flat
+        d, c = clf.input_dim, clf.num_classes
+        self.x = torch.zeros(batch, d, dtype=torch.float32, device=dev)
+        self.y = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.logits = torch.empty(batch, c, dtype=torch.float32, device=dev)
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        group = optimizer.param_groups[0]
+        ast = optimizer.flat_state(st.flat)
+        b1, b2 = group["betas"]
+        self.key = (float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]))
+        cfg = _lib.AdamConfig(*self.key)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self._ws = st.workspace                      # the graph addresses this workspace: keep it alive, detect a re-allocation
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+
+        def call():
+            check(lib.ae_mlp_train_step(ptr(st.flat.data), ptr(st.flat.grad), ptr(st.running), ptr(st.steps), ptr(self.x), ptr(self.y),
+                                        seed, ptr(self.seed_dev), float(clf.net[3].p), batch, d, c, ptr(self.logits), ptr(self.loss),
+                                        ptr(self.correct), st.ws_ptr, st.ws_bytes, C.byref(cfg), ptr(ast["m"]), ptr(ast["v"]),
+                                        ptr(ast["step"]), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        with torch.cuda.stream(stream):
+            # (no warm-up launch: it would be a real optimizer step; the kernels allocate nothing)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=stream):
+                call()
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        for p_, g in zip(st.flat.params, st.flat.grad_views(st.flat.grad)):
+            if p_.requires_grad:
+                p_.grad = g
+
+    def valid(self) -> bool:
+        st = self._st
+        group = self.opt.param_groups[0]
+        b1, b2 = group["betas"]
+        key = (float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]))
+        return st.flat is self._flat and st.workspace is self._ws and st.flat.aliased() and key == self.key
+
+    def run(self):
+        """Replay on the current stream; loss [1], correct [1] and logits are valid afterwards (stream-ordered)."""
+        self.graph.replay()
+        self._flat.generation += 1

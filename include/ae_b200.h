@@ -138,6 +138,11 @@ int ae_conv2d_s2_wgrad(const ae_conv_geom_t* g, const ae_operand_t* big, const a
                        float* dw, void* partials, size_t partials_bytes, int precision, int backend,
                        ae_stream_t stream);
 
+/* torch.optim.Adam hyper-parameters (NB:2654, NB:3461) */
+typedef struct ae_adam_config {
+  float lr, beta1, beta2, eps, weight_decay;
+} ae_adam_config_t;
+
 /* ------------------------------------------------------------------------------------------
  * Thin (3-channel) layers: Conv2d(3,32) NB:504 and ConvTranspose2d(32,3)+Sigmoid NB:628-629.
  * thin = [B,3,64,64] NCHW fp32 (the reference's image layout), wide = [B,32,32,32] NHWC.
@@ -219,6 +224,14 @@ int ae_mlp_fwd_bwd_ce(const float* params, float* grads, float* bn_running /*[me
                       int training, float* logits, float* loss /*[1]*/, int* correct /*[1]*/,
                       void* workspace, size_t workspace_bytes, ae_stream_t stream);
 size_t ae_mlp_workspace_bytes(int batch, int input_dim, int num_classes);
+/* One MLP training step of the reference loop (NB:3476-3482) -- forward + CE + backward launch, then the fused Adam launch
+ * (torch.optim.Adam semantics, coupled weight decay) -- with nothing baked in that changes from step to step: the dropout
+ * seed of a launch is dropout_seed + seed_dev[0] and the launch advances seed_dev[0]; num_batches_tracked (bn_steps,
+ * int64[2]) is bumped on the device.  Meant to be captured in a CUDA graph and replayed per batch. */
+int ae_mlp_train_step(float* params, float* grads, float* bn_running, int64_t* bn_steps, const float* x, const int64_t* labels,
+                      uint64_t dropout_seed, uint64_t* seed_dev, float dropout_p, int batch, int input_dim, int num_classes,
+                      float* logits, float* loss, int* correct, void* workspace, size_t workspace_bytes,
+                      const ae_adam_config_t* adam, float* adam_m, float* adam_v, int* step_dev, ae_stream_t stream);
 int ae_mlp_forward_eval(const float* params, const float* bn_running, const float* x, int batch, int input_dim,
                         int num_classes, float* logits, int64_t* argmax /*or NULL*/, ae_stream_t stream);
 /* Backward of a preceding training-mode ae_mlp_fwd_bwd_ce call made with labels == NULL (forward only,
@@ -311,9 +324,6 @@ int ae_eval_step(ae_engine_t* e, const float* x, const int64_t* labels, int batc
  * ---------------------------------------------------------------------------------------- */
 typedef struct ae_step_graph ae_step_graph_t;
 typedef struct ae_dp_comm ae_dp_comm_t;
-typedef struct ae_adam_config {
-  float lr, beta1, beta2, eps, weight_decay;
-} ae_adam_config_t;
 int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels, int batch, float alpha,
                           float* loss_out, float* flat_params, float* flat_grads, float* adam_m,
                           float* adam_v, int64_t flat_len, const ae_adam_config_t* adam, int* step_dev,

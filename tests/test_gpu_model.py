@@ -566,3 +566,51 @@ def test_invalidate_after_raw_parameter_writes():
             pa.data.copy_(pb.data)                                 # raw write: no version bump
         a.engine().invalidate()
         assert torch.equal(a.enc(x), zb)
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8"])
+@pytest.mark.parametrize("batch", [64, 37])
+def test_mlp_train_step_graph_matches_oracle_loop(batch, cluster, monkeypatch):
+    """MLPTrainStep (NB:3476-3482 as a replayed two-launch graph: cluster kernel + fused Adam with weight decay 1e-4) against
+    the oracle loop over several steps, dropout switched off so both sides see the same network; every cluster size of the
+    kernel (the library picks it by batch size; AE_B200_MLP_CLUSTER forces it)."""
+    monkeypatch.setenv("AE_B200_MLP_CLUSTER", cluster)
+    seed, lr, wd, steps = 41, 1e-3, 1e-4, 5
+    st = seeded.seeded_state(seeded.mlp_state_shapes(64, 10), seed)
+    rs = np.random.RandomState(batch)
+    xs = [torch.from_numpy(rs.standard_normal((batch, 64)).astype(np.float32)) for _ in range(steps)]
+    ys = [seeded.seeded_labels(batch, seed + i) for i in range(steps)]
+    keep = None                                   # the oracle's 'no dropout' (an explicit mask would be scaled by 1/0.7)
+    ref_state, opt_ref = {k: v.clone() for k, v in st.items()}, {}
+    ref_losses, ref_after_first = [], None
+    for i in range(steps):
+        ref_losses.append(float(tp.mlp_train_step(ref_state, opt_ref, xs[i], ys[i], lr, wd, keep)[0]))
+        if i == 0:
+            ref_after_first = {k: v.clone() for k, v in ref_state.items()}
+    clf = ae_b200.MLP(64, 10)
+    clf.load_state_dict(st)
+    clf = clf.to(gu.dev()).train()
+    clf.net[3].p = 0.0
+    clf._state.prepare(gu.dev(), batch)
+    opt = ae_b200.Adam(clf.parameters(), lr=lr, weight_decay=wd)
+    step = ae_b200.MLPTrainStep(clf, opt, batch)
+    losses, after_first = [], None
+    for i in range(steps):
+        step.x.copy_(xs[i]); step.y.copy_(ys[i])
+        step.run()
+        losses.append(float(step.loss))
+        if i == 0:
+            after_first = {k: v.detach().clone() for k, v in clf.state_dict().items()}
+    torch.cuda.synchronize()
+    # step 0 sees identical weights; afterwards Adam's first updates are ~lr * sign(g), so entries with |g| ~ 0 may move the
+    # other way in another arithmetic and the trajectories separate slightly (DESIGN.md 'Numerics')
+    assert abs(losses[0] - ref_losses[0]) <= 1e-5 * max(1.0, abs(ref_losses[0])), (losses, ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 5e-3 * max(1.0, abs(b)), (losses, ref_losses)
+    sd = clf.state_dict()
+    assert int(sd["net.1.num_batches_tracked"]) == steps and int(sd["net.5.num_batches_tracked"]) == steps
+    for k in ("net.1.running_mean", "net.1.running_var", "net.5.running_mean", "net.5.running_var"):
+        assert gu.rel(after_first[k], ref_after_first[k]) <= 1e-4, k       # the first step's batch statistics
+    # the first Adam step moves every weight by ~lr: all of them within 2 lr of the oracle, nearly all of them the same way
+    d = (after_first["net.4.weight"].cpu() - ref_after_first["net.4.weight"]).abs()
+    assert float(d.max()) <= 2.01 * lr and float((d > 0.1 * lr).float().mean()) <= 1e-2
