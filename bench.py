@@ -722,11 +722,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the stand-alone kernel timing and the inference leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the end-to-end leg (its number is then meaningless)")
+    ap.add_argument("--roofline-only", action="store_true", help="profiling aid: only the stand-alone launches of the roofline kernel (for ncu --set full)")
     ap.add_argument("--no-extras", action="store_true", help="skip the torch-GPU baseline, drop-in loop, MLP and global-batch-4096 legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.roofline_only:
+        torch.cuda.set_device(0)
+        print(json.dumps(kernel_roofline(torch.device("cuda", 0), args.batch, args.precision)))
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -76,5 +76,31 @@ def full(path):
               f"{get(r, 'launch__registers_per_thread'):5.0f} {get(r, 'launch__grid_size'):7.0f}  {short(r[col['Kernel Name']])}")
 
 
+def traffic(path, out_json, precision="fp32"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches) -> profiles/r2_roofline_traffic.json"""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = []
+    for r in data:
+        b = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = col[name]
+            b += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+        tot.append(b)
+    d = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    d[precision] = sum(tot) / len(tot)
+    d[precision + "_source"] = f"{os.path.basename(path)}: ncu --set full, {len(tot)} launches of {short(data[0][col['Kernel Name']])}"
+    json.dump(d, open(out_json, "w"), indent=1)
+    print(d)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "fp32")
+        sys.exit(0)
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

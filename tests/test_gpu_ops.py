@@ -513,3 +513,49 @@ def test_linear_fwd_bwd_with_flatten_permutation():
     assert gu.rel(gu.nchw(da).cpu(), a4.grad) <= 1e-5
     assert gu.rel(dw, wr.grad) <= 1e-5
     assert gu.rel(db, br.grad) <= 1e-5
+
+
+def _guarded(shape, dtype=torch.float32):
+    """Tensor of `shape` inside a larger allocation whose 16 KB before and after it hold a sentinel: compute-sanitizer is
+    closed on this pool (gpurun refuses it), so out-of-bounds writes of the TMA stores / epilogues are looked for this way."""
+    n = int(np.prod(shape))
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    guard = 16384 // itemsize
+    buf = torch.full((n + 2 * guard,), 7, dtype=torch.uint8 if dtype == torch.uint8 else dtype, device=gu.dev())
+    if dtype != torch.uint8:
+        buf.fill_(-12345.0)
+    t = buf[guard:guard + n].view(*shape)
+
+    def intact():
+        ref = 7 if dtype == torch.uint8 else -12345.0
+        return bool((buf[:guard] == ref).all()) and bool((buf[guard + n:] == ref).all())
+    return t, intact
+
+
+@pytest.mark.parametrize("gen", ["1", "2"])
+@pytest.mark.parametrize("prec", gu.PRECISIONS)
+@pytest.mark.parametrize("shape", [(3, 8, 64, 128), (5, 4, 128, 256), (33, 16, 32, 64), (1, 4, 128, 256), (150, 4, 128, 256)])
+def test_rowgemm_writes_stay_inside_the_output(shape, prec, gen, monkeypatch):
+    """Ragged last tiles (M not a multiple of 128 or 32 rows): the tensor-map stores of the second generation must clip, the
+    per-lane stores of the first generation must be masked; every valid element must be written."""
+    if "tc" not in gu.BACKENDS:
+        pytest.skip("tcgen05 path only")
+    monkeypatch.setenv("AE_B200_ROWGEMM", gen)
+    b, hs, cb, cs = shape
+    d = gu.dev()
+    w = torch.randn(cs, cb, 3, 3, device=d) * 0.05
+    pf, pd = gu.pack_conv(w, cs, cb, prec, "tc")
+    g = _geom(b, hs, cb, cs)
+    for fam in ("fwd", "dgrad"):
+        cin, hin, oshape, oc = (cb, 2 * hs, (b, hs, hs, cs), cs) if fam == "fwd" else (cs, hs, (b, 2 * hs, 2 * hs, cb), cb)
+        a = torch.randn(b, hin, hin, cin, device=d)
+        op, _keep = gu.conv_operand("tc", prec, cin, a)
+        fn = gu.lib().ae_conv2d_s2_fwd if fam == "fwd" else gu.lib().ae_conv2d_s2_dgrad
+        out, intact = _guarded(oshape)
+        bias = torch.zeros(oc, device=d)
+        stats = torch.zeros(2 * oc, dtype=torch.float64, device=d)
+        ep = gu.epilogue(_lib.EPI_BIAS_STATS, bias, None, None, stats)
+        _lib.check(fn(C.byref(g), C.byref(op), gu.p(pf if fam == "fwd" else pd), C.byref(ep), gu.p(out), gu.PREC[prec], gu.BACK["tc"], gu.stream()))
+        torch.cuda.synchronize()
+        assert intact(), f"{fam}: wrote outside the output tensor"
+        assert not bool((out == -12345.0).any()), f"{fam}: left output elements unwritten"
