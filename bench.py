@@ -228,7 +228,7 @@ def _time_loop(step, xs, ys, steps, warmup):
         last = step(xs[i % len(xs)], ys[i % len(ys)])
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / steps, float(last)
+    return e0.elapsed_time(e1) * 1e-3 / steps, float(last.detach())
 
 
 def torch_gpu_baseline(dev, B, xs, ys, steps=50, warmup=10):
@@ -258,6 +258,16 @@ def dropin_loop(dev, B, xs, ys, precision, backend, steps=50, warmup=10):
     t, loss = _time_loop(step, xs, ys, steps, warmup)
     return {"value": B / t, "unit": "images/s", "ms_per_step": t * 1e3, "steps": steps, "final_loss": loss,
             "what": "model(imgs); alpha*mse + ce; loss.backward(); optimizer.step() with ae_b200 modules (no step graph)"}
+
+
+def full_pipeline(dev):
+    """BASELINE configs[2]: AE pre-training, latent extraction and the MLP on frozen latents over a synthetic, class-structured
+    27,000-image EuroSAT-shaped set (18,900 / 4,050 / 4,050), bf16 mode, everything on the device (scripts/full_pipeline.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ae_full_pipeline", os.path.join(ROOT, "scripts", "full_pipeline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.run(precision="bf16", dev=dev)
 
 
 def mlp_train_rate(dev, steps=200, batch=64):
@@ -647,6 +657,7 @@ def run_ours(args):
             guarded("torch_gpu_baseline", lambda: torch_gpu_baseline(dev, B, xs_d, ys_d))
             guarded("dropin_loop", lambda: dropin_loop(dev, B, xs_d, ys_d, args.precision, args.backend))
             guarded("mlp_train", lambda: mlp_train_rate(dev))
+            guarded("full_pipeline_bf16", lambda: full_pipeline(dev))
         barrier()
         guarded("dp_global_4096", lambda: dp_global_batch(dev, world, rank, comm, args, 4096))
         if world > 1:

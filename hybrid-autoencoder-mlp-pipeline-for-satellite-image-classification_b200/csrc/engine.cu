@@ -118,7 +118,7 @@ struct ae_engine {
   size_t partial_side_bytes = 0;
   // data-parallel step being captured: gradient exchange interleaved with the backward pass
   ae_dp_comm_t* step_comm = nullptr;
-  bool dp_single = false;             // data-parallel variant: no exchange inside the backward pass, one allreduce of the flat buffer after it
+  bool dp_single = false;             // data parallel over peer memory: no NCCL exchange inside the backward pass (k_dp_adam does it all)
   bool defer_conv1_wgrad = false;     // the captured step runs conv1's weight gradient beside Adam + re-pack of everything else
   bool stats_cleared = false;         // the fused step zeroed every statistic accumulator in one memset: the parts skip theirs
   // pointers remembered between forward and backward
@@ -936,14 +936,12 @@ int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels,
   const int64_t c1 = 864;   // conv1.weight = the first tensor of the encoder part
   const bool split_tail = !e->simt && e->part[AE_PART_ENC].params == flat_params && flat_len > c1;
   e->defer_conv1_wgrad = split_tail;
-  const char* tail_env = getenv("AE_B200_DP_TAIL");
-  const int dp_tail = tail_env ? atoi(tail_env) : 0;
   // peers attached for exactly these flat buffers (ae_dp_peers_attach): reduce-scatter + Adam + all-gather as ONE kernel over
   // NVLink peer memory instead of NCCL allreduces + Adam (AE_B200_DP_FUSED=0 keeps the NCCL form)
   const char* fused_env = getenv("AE_B200_DP_FUSED");
   const DpAttachment* peers = comm && split_tail && !(fused_env && atoi(fused_env) == 0)
                                   ? dp_find_attachment(comm, flat_params, flat_grads, flat_len) : nullptr;
-  e->dp_single = comm != nullptr && split_tail && (dp_tail == 2 || peers != nullptr);
+  e->dp_single = peers != nullptr;
   int rc = ae_train_step(e, x, labels, batch, alpha, loss_out, stream);
   e->step_comm = nullptr;
   e->defer_conv1_wgrad = false;
@@ -963,35 +961,14 @@ int ae_step_graph_capture(ae_engine_t* e, const float* x, const int64_t* labels,
     return 0;
   };
   if (rc == 0 && peers) {
-    // as on one GPU: conv1's weight gradient beside the exchange + update + re-pack of every other parameter; its own 864
-    // weights get a (tiny) exchange round of their own after the join
-    auto fused = [&](int64_t lo, int64_t n, int bump) {
-      return dp_adam_fused(comm, peers, adam_m, adam_v, lo, n, adam->lr, adam->beta1, adam->beta2, adam->eps, adam->weight_decay,
-                           step_dev, bump, st);
-    };
-    rc = fork_side(e, st);
-    if (rc == 0) rc = conv1_wgrad(e, batch, e->side);
-    if (rc == 0) rc = fused(c1, flat_len - c1, 0);
-    if (rc == 0) rc = pack_all_parts(e, st);
-    if (rc == 0) rc = join_side(e, st);
-    if (rc == 0) rc = fused(0, c1, 1);
-  } else if (rc == 0 && split_tail && comm && dp_tail == 2) {
-    // variant: ONE allreduce of the whole flat gradient buffer after the backward pass (SURVEY 8e as written)
+    // ONE exchange round after the last gradient (conv1's weights).  Measured on 2 and 8 GPUs: running conv1's weight gradient
+    // beside a first round over everything else and its 864 weights in a round of their own is no faster (0.718 / 0.749 ms
+    // against 0.713 / 0.747 ms): what the ranks wait for is each other, not the exchange.
     rc = conv1_wgrad(e, batch, st);
-    if (rc == 0) rc = ae_dp_allreduce(comm, flat_grads, flat_len, st);
-    if (rc == 0) rc = adam_range(0, flat_len, 1);
+    if (rc == 0)
+      rc = dp_adam_fused(comm, peers, adam_m, adam_v, 0, flat_len, adam->lr, adam->beta1, adam->beta2, adam->eps, adam->weight_decay,
+                         step_dev, 1, st);
     if (rc == 0) rc = pack_all_parts(e, st);
-  } else if (rc == 0 && split_tail && comm && dp_tail == 1) {
-    // variant: conv1's weight gradient on the side branch, beside the encoder's gradient exchange (side2) and then beside
-    // Adam + re-pack of every other parameter; the exchange of its own 864 gradients is left exposed at the end
-    rc = fork_side(e, st);
-    if (rc == 0) rc = conv1_wgrad(e, batch, e->side);
-    if (rc == 0) rc = link(e->ev_join2, e->side2, st);       // decoder, head, encoder (without conv1.weight) are exchanged
-    if (rc == 0) rc = adam_range(c1, flat_len - c1, 0);
-    if (rc == 0) rc = pack_all_parts(e, st);
-    if (rc == 0) rc = join_side(e, st);
-    if (rc == 0) rc = ae_dp_allreduce(comm, flat_grads, c1, st);
-    if (rc == 0) rc = adam_range(0, c1, 1);
   } else if (rc == 0 && split_tail && comm) {
     rc = conv1_wgrad(e, batch, st);
     // every exchange issued so far (decoder, head, encoder without conv1.weight) is complete before Adam reads it

@@ -33,15 +33,9 @@ def structured_u8(n_per_class, seed, dev):
     return u8[perm].contiguous(), labels[perm].contiguous()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--precision", default="bf16")
-    ap.add_argument("--ae-epochs", type=int, default=20)
-    ap.add_argument("--mlp-epochs", type=int, default=30)
-    ap.add_argument("--ae-batch", type=int, default=64)       # the reference's batch size (NB:418)
-    ap.add_argument("--per-class", type=int, default=2700)
-    a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+def run(precision="bf16", ae_epochs=20, mlp_epochs=30, ae_batch=64, per_class=2700, dev=None):
+    a = argparse.Namespace(precision=precision, ae_epochs=ae_epochs, mlp_epochs=mlp_epochs, ae_batch=ae_batch, per_class=per_class)
+    dev = dev or torch.device("cuda", 0)
     imgs, labels = structured_u8(a.per_class, 0, dev)
     n = imgs.shape[0]
     n_tr, n_va = int(0.7 * n), int(0.15 * n)                  # NB:306-308
@@ -52,12 +46,23 @@ def main():
     res = ae_b200.pipeline.run_pipeline(tr, va, te, alpha=35.0, ae_lr=5e-3, mlp_lr=1e-4, ae_epochs=a.ae_epochs, ae_patience=15,
                                         mlp_epochs=a.mlp_epochs, ae_batch=a.ae_batch, precision=a.precision, generator=g, seed=2)
     ae_imgs = res["ae"]["epochs"] * (len(tr) + len(va))
-    print(json.dumps({"config": "full pipeline, synthetic class-structured set", "images": n, "splits": [len(tr), len(va), len(te)],
+    return ({"config": "full pipeline, synthetic class-structured set", "images": n, "splits": [len(tr), len(va), len(te)],
                       "precision": a.precision, "ae_batch": a.ae_batch, "ae_epochs_run": res["ae"]["epochs"],
                       "mlp_epochs": a.mlp_epochs, "seconds": res["seconds"],
                       "ae_images_per_s": ae_imgs / res["seconds"]["autoencoder"],
                       "ae_final_train_loss": res["ae"]["train_curve"][-1], "ae_best_val_loss": res["ae"]["best_val_loss"],
-                      "mlp_best_val_acc": res["mlp"]["best_val_acc"], "test_acc": res["test_acc"]}))
+                      "mlp_best_val_acc": res["mlp"]["best_val_acc"], "test_acc": res["test_acc"]})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--ae-epochs", type=int, default=20)
+    ap.add_argument("--mlp-epochs", type=int, default=30)
+    ap.add_argument("--ae-batch", type=int, default=64)       # the reference's batch size (NB:418)
+    ap.add_argument("--per-class", type=int, default=2700)
+    a = ap.parse_args()
+    print(json.dumps(run(a.precision, a.ae_epochs, a.mlp_epochs, a.ae_batch, a.per_class)))
 
 
 if __name__ == "__main__":
