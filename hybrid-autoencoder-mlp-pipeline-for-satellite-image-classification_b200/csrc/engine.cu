@@ -492,7 +492,7 @@ static int pack_all_parts(ae_engine* e, cudaStream_t st) {
   auto conv = [&](const Part& P, MidLayer& m) {
     PackJob& j = J.job[n++];
     j.kind = PACK_CONV; j.src = P.P(m.w); j.dst = m.pk_fwd; j.dst2 = m.pk_dgrad;
-    j.a = m.g.Cs; j.b = m.g.Cb; j.c = e->nsplit; j.total = 2 * 9 * m.g.Cs * m.g.Cb;
+    j.a = m.g.Cs; j.b = m.g.Cb; j.c = e->nsplit; j.total = 2 * 9 * m.g.Cs * m.g.Cb / 8;
   };
   auto lin = [&](const float* w, int N, int K, int permC, int permHW, int kind, float* dst) {
     PackJob& j = J.job[n++];

@@ -4,34 +4,37 @@
 
 namespace ae {
 
-// One element (idx in [0, 2*9*Cs*Cb)) of the conv weight pack: w [Cs][Cb][3][3] fp32 -> swizzled bf16 (hi[, lo]) tiles
-// for both row-GEMM orientations (layout described in tma_gemm.cu).
-__device__ __forceinline__ void pack_conv_elem(int idx, const float* __restrict__ w, int Cs, int Cb, int nsplit,
-                                               uint8_t* __restrict__ fwd, uint8_t* __restrict__ dgrad) {
+// Eight consecutive K elements (one 16-byte chunk of a swizzled row; idx8 in [0, 2*9*Cs*Cb/8)) of the conv weight pack:
+// w [Cs][Cb][3][3] fp32 -> swizzled bf16 (hi[, lo]) tiles for both row-GEMM orientations (layout described in tma_gemm.cu).
+// One 16-byte store per plane instead of eight 2-byte stores.
+__device__ __forceinline__ void pack_conv_chunk(int idx8, const float* __restrict__ w, int Cs, int Cb, int nsplit,
+                                                uint8_t* __restrict__ fwd, uint8_t* __restrict__ dgrad) {
   const int KCf = Cb >= 64 ? 64 : 32, NTf = Cs >= 64 ? 64 : 32;
   const int NTd = Cb >= 64 ? 64 : 32;
-  const int nf = Cs * 9 * Cb;
-  float v;
+  const int nf8 = Cs * 9 * Cb / 8;
+  float v[8];
   uint8_t* base;
   int r, j, NT, KC;
   size_t tile;
-  if (idx < nf) {
-    const int k = idx % (9 * Cb), n = idx / (9 * Cb);   // n = cs, k = tap*Cb + cb
+  if (idx8 < nf8) {
+    const int k = (idx8 % (9 * Cb / 8)) * 8, n = idx8 / (9 * Cb / 8);   // n = cs, k = tap*Cb + cb (8 consecutive cb)
     const int tap = k / Cb, cb = k - tap * Cb;
-    v = w[((size_t)n * Cb + cb) * 9 + tap];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = w[((size_t)n * Cb + cb + u) * 9 + tap];
     KC = KCf; NT = NTf;
     const int kc = k / KC; j = k - kc * KC;
     r = n % NT; tile = (size_t)(n / NT) * (9 * Cb / KC) + kc; base = fwd;
   } else {
-    const int i2 = idx - nf;
-    const int k = i2 % (9 * Cs), n = i2 / (9 * Cs);     // n = cb, k = slot*Cs + cs
+    const int i2 = idx8 - nf8;
+    const int k = (i2 % (9 * Cs / 8)) * 8, n = i2 / (9 * Cs / 8);       // n = cb, k = slot*Cs + cs (8 consecutive cs)
     const int slot = k / Cs, cs = k - slot * Cs;        // slot 0: phase 0; 1-2: phase 1; 3-4: phase 2; 5-8: phase 3
     int ky, kx;
     if (slot == 0) { ky = 1; kx = 1; }
     else if (slot <= 2) { ky = 1; kx = slot == 1 ? 0 : 2; }
     else if (slot <= 4) { ky = slot == 3 ? 0 : 2; kx = 1; }
     else { const int t = slot - 5; ky = (t >> 1) ? 2 : 0; kx = (t & 1) ? 2 : 0; }
-    v = w[((size_t)cs * Cb + n) * 9 + ky * 3 + kx];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = w[((size_t)(cs + u) * Cb + n) * 9 + ky * 3 + kx];
     KC = 64; NT = NTd;
     const int kc = k / KC; j = k - kc * KC;
     r = n % NT; tile = (size_t)(n / NT) * (9 * Cs / KC) + kc; base = dgrad;
@@ -39,10 +42,22 @@ __device__ __forceinline__ void pack_conv_elem(int idx, const float* __restrict_
   const int rowb = KC * 2;
   const int swz = rowb == 128 ? (r & 7) : ((r >> 1) & 3);
   const size_t tile_bytes = (size_t)nsplit * NT * rowb;
-  const size_t off = tile * tile_bytes + (size_t)r * rowb + (size_t)((((j >> 3) ^ swz) << 4) + (j & 7) * 2);
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
-  if (nsplit == 2) *reinterpret_cast<__nv_bfloat16*>(base + off + (size_t)NT * rowb) = __float2bfloat16_rn(v - __bfloat162float(hi));
+  const size_t off = tile * tile_bytes + (size_t)r * rowb + (size_t)(((j >> 3) ^ swz) << 4);
+  __nv_bfloat162 h[4];
+  float lo[8];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    h[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+    lo[2 * u] = v[2 * u] - __bfloat162float(h[u].x);
+    lo[2 * u + 1] = v[2 * u + 1] - __bfloat162float(h[u].y);
+  }
+  *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(h);
+  if (nsplit == 2) {
+    __nv_bfloat162 l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) l[u] = __floats2bfloat162_rn(lo[2 * u], lo[2 * u + 1]);
+    *reinterpret_cast<uint4*>(base + off + (size_t)NT * rowb) = *reinterpret_cast<const uint4*>(l);
+  }
 }
 
 // Linear weight w [N][K] (torch).  perm(k) = (k % permC) * permHW + k / permC maps an NHWC flatten index to the
@@ -78,7 +93,7 @@ struct PackJob {
   void* dst;
   void* dst2;
   int a, b, c, d, e;        // CONV: Cs, Cb, nsplit.  LINEAR: N, K, permC, permHW, lkind.  PERMUTE: n, permC, permHW
-  int total;                // elements
+  int total;                // work items: 8-element chunks (CONV) or elements
   int first_block;          // first block of this job in the fused launch
 };
 static constexpr int PACK_MAX_JOBS = 16;

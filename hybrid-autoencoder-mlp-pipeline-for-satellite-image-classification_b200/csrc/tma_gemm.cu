@@ -488,9 +488,9 @@ static inline int kc_fwd(int Cb) { return Cb >= 64 ? 64 : 32; }
 
 __global__ void k_tma_pack_conv(const float* __restrict__ w, int Cs, int Cb, int nsplit, uint8_t* __restrict__ fwd,
                                 uint8_t* __restrict__ dgrad) {
-  const int total = 2 * 9 * Cs * Cb;
+  const int total = 2 * 9 * Cs * Cb / 8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
-    pack_conv_elem(idx, w, Cs, Cb, nsplit, fwd, dgrad);
+    pack_conv_chunk(idx, w, Cs, Cb, nsplit, fwd, dgrad);
 }
 
 // Every re-layout job of one optimizer step in a single launch.
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(256) k_pack_all(const __grid_constant__ PackJo
   const PackJob& J = jobs.job[j];
   const int nblk = (j + 1 < jobs.n ? jobs.job[j + 1].first_block : (int)gridDim.x) - J.first_block;
   for (int idx = ((int)blockIdx.x - J.first_block) * blockDim.x + threadIdx.x; idx < J.total; idx += nblk * blockDim.x) {
-    if (J.kind == PACK_CONV) pack_conv_elem(idx, J.src, J.a, J.b, J.c, (uint8_t*)J.dst, (uint8_t*)J.dst2);
+    if (J.kind == PACK_CONV) pack_conv_chunk(idx, J.src, J.a, J.b, J.c, (uint8_t*)J.dst, (uint8_t*)J.dst2);
     else if (J.kind == PACK_LINEAR) pack_linear_elem(idx, J.src, J.a, J.b, J.c, J.d, J.e, (float*)J.dst);
     else permute_elem(idx, J.src, J.b, J.c, (float*)J.dst);
   }
@@ -526,7 +526,7 @@ size_t tma_packed_bytes(int Cs, int Cb, int nsplit) { return (size_t)9 * Cs * Cb
 int tma_pack_conv(const float* w, int Cs, int Cb, int nsplit, void* fwd, void* dgrad, cudaStream_t st) {
   AE_CHECK(Cs % 64 == 0 && Cb % 32 == 0, "tma_pack_conv: Cs=%d must be a multiple of 64 and Cb=%d of 32", Cs, Cb);
   AE_CHECK((((uintptr_t)fwd | (uintptr_t)dgrad) & 15) == 0, "tma_pack_conv: packed buffers must be 16-byte aligned");
-  const int total = 2 * 9 * Cs * Cb;
+  const int total = 2 * 9 * Cs * Cb / 8;
   int blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_tma_pack_conv<<<blocks, 256, 0, st>>>(w, Cs, Cb, nsplit, (uint8_t*)fwd, (uint8_t*)dgrad);

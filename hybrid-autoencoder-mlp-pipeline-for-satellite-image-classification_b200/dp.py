@@ -67,13 +67,23 @@ def attach_peers(comm: Communicator, model) -> bool:
     flags = torch.zeros(_lib.DP_FLAG_BYTES // 4, dtype=torch.int32, device=dev)
     torch.cuda.synchronize(dev)
     mine = []
-    for t in (flat.data, flat.grad, flags):
-        h = (C.c_uint8 * _lib.DP_IPC_HANDLE_BYTES)()
-        off = C.c_int64()
-        check(lib.ae_dp_ipc_export(C.c_void_p(t.data_ptr()), h, C.byref(off)))
-        mine.append((bytes(h), int(off.value)))
+    try:
+        for t in (flat.data, flat.grad, flags):
+            h = (C.c_uint8 * _lib.DP_IPC_HANDLE_BYTES)()
+            off = C.c_int64()
+            check(lib.ae_dp_ipc_export(C.c_void_p(t.data_ptr()), h, C.byref(off)))
+            mine.append((bytes(h), int(off.value)))
+    except RuntimeError as ex:        # e.g. an allocator whose blocks cannot be exported (expandable segments)
+        mine = str(ex)
     everyone = [None] * comm.world
     dist.all_gather_object(everyone, mine)
+    failed = [(r, m) for r, m in enumerate(everyone) if isinstance(m, str)]
+    if failed:                        # every rank sees the same list: all of them keep the NCCL form
+        if comm.rank == 0:
+            import warnings
+            warnings.warn(f"ae_b200.dp: peer memory not available (rank {failed[0][0]}: {failed[0][1]}); the step exchanges "
+                          "gradients with NCCL allreduces instead of the fused peer-memory kernel")
+        return False
     handles = (C.c_uint8 * (comm.world * 3 * _lib.DP_IPC_HANDLE_BYTES))()
     offsets = (C.c_int64 * (comm.world * 3))()
     for r, bufs in enumerate(everyone):
