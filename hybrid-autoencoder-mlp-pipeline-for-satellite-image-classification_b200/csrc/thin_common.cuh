@@ -1,4 +1,4 @@
-// Shared pieces of the thin-layer kernels (thin.cu: CUDA cores; thin_tc.cu: tcgen05).
+// Shared pieces of the 3-channel-layer kernels (thin.cu).
 #pragma once
 #include "tc_common.cuh"
 
