@@ -4,6 +4,25 @@
 
 namespace ae {
 
+// Data-gradient weight pack ("group pack").  Per (n-tile, K chunk c) a block of 9 tiles, ordered so that the tiles one MMA of
+// the second-generation row GEMM stacks along N are one contiguous region -- [hi plane of its tiles][lo plane of its tiles] --
+// and arrive with ONE cp.async.bulk:
+//   group 0 (shift (0,0)): slots 0, 2      group 1 (shift (0,0)): slots 8, 4      group 2 (shift (0,1)): slots 1, 7
+//   group 3 (shift (1,0)): slots 6, 3      group 4 (shift (1,1)): slot 5
+// (slot = position in the phase-stacked tap order: 0: phase 0; 1-2: phase 1; 3-4: phase 2; 5-8: phase 3).
+// dg_pack_plane_offset: byte offset of plane `pl` of the tile in `slot` inside the 9-tile block; plane_bytes = NT * 128.
+__host__ __device__ __forceinline__ int dg_pack_group_of_slot(int slot, int* t) {
+  const int g = slot == 0 || slot == 2 ? 0 : slot == 8 || slot == 4 ? 1 : slot == 1 || slot == 7 ? 2 : slot == 6 || slot == 3 ? 3 : 4;
+  *t = (slot == 2 || slot == 4 || slot == 7 || slot == 3) ? 1 : 0;
+  return g;
+}
+__host__ __device__ __forceinline__ size_t dg_pack_plane_offset(int slot, int pl, int nsplit, size_t plane_bytes) {
+  int t;
+  const int g = dg_pack_group_of_slot(slot, &t);
+  const int ntl = g == 4 ? 1 : 2;
+  return ((size_t)(2 * g) * nsplit + (size_t)pl * ntl + t) * plane_bytes;      // groups 0..3 hold two tiles each
+}
+
 // Eight consecutive K elements (one 16-byte chunk of a swizzled row; idx8 in [0, 2*9*Cs*Cb/8)) of the conv weight pack:
 // w [Cs][Cb][3][3] fp32 -> swizzled bf16 (hi[, lo]) tiles for both row-GEMM orientations (layout described in tma_gemm.cu).
 // One 16-byte store per plane instead of eight 2-byte stores.
@@ -15,7 +34,8 @@ __device__ __forceinline__ void pack_conv_chunk(int idx8, const float* __restric
   float v[8];
   uint8_t* base;
   int r, j, NT, KC;
-  size_t tile;
+  size_t tile = 0, dg_off_hi = 0, dg_off_lo = 0;
+  bool is_dgrad = false;
   if (idx8 < nf8) {
     const int k = (idx8 % (9 * Cb / 8)) * 8, n = idx8 / (9 * Cb / 8);   // n = cs, k = tap*Cb + cb (8 consecutive cb)
     const int tap = k / Cb, cb = k - tap * Cb;
@@ -36,13 +56,23 @@ __device__ __forceinline__ void pack_conv_chunk(int idx8, const float* __restric
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = w[((size_t)(cs + u) * Cb + n) * 9 + ky * 3 + kx];
     KC = 64; NT = NTd;
-    const int kc = k / KC; j = k - kc * KC;
-    r = n % NT; tile = (size_t)(n / NT) * (9 * Cs / KC) + kc; base = dgrad;
+    const int c = cs / KC; j = cs - c * KC;
+    r = n % NT; base = dgrad;
+    const int cpt = Cs / KC;
+    const size_t plane_bytes = (size_t)NT * 128;
+    const size_t blk = ((size_t)(n / NT) * cpt + c) * 9 * nsplit * plane_bytes;
+    const int swz_d = r & 7;
+    const size_t in_plane = (size_t)r * 128 + (size_t)(((j >> 3) ^ swz_d) << 4);
+    dg_off_hi = blk + dg_pack_plane_offset(slot, 0, nsplit, plane_bytes) + in_plane;
+    dg_off_lo = blk + dg_pack_plane_offset(slot, 1, nsplit, plane_bytes) + in_plane;
+    is_dgrad = true;
   }
   const int rowb = KC * 2;
   const int swz = rowb == 128 ? (r & 7) : ((r >> 1) & 3);
   const size_t tile_bytes = (size_t)nsplit * NT * rowb;
-  const size_t off = tile * tile_bytes + (size_t)r * rowb + (size_t)(((j >> 3) ^ swz) << 4);
+  size_t off = tile * tile_bytes + (size_t)r * rowb + (size_t)(((j >> 3) ^ swz) << 4);
+  size_t off_lo = off + (size_t)NT * rowb;
+  if (is_dgrad) { off = dg_off_hi; off_lo = dg_off_lo; }
   __nv_bfloat162 h[4];
   float lo[8];
 #pragma unroll
@@ -56,7 +86,7 @@ __device__ __forceinline__ void pack_conv_chunk(int idx8, const float* __restric
     __nv_bfloat162 l[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) l[u] = __floats2bfloat162_rn(lo[2 * u], lo[2 * u + 1]);
-    *reinterpret_cast<uint4*>(base + off + (size_t)NT * rowb) = *reinterpret_cast<const uint4*>(l);
+    *reinterpret_cast<uint4*>(base + off_lo) = *reinterpret_cast<const uint4*>(l);
   }
 }
 

@@ -86,13 +86,13 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 //   shift (0,1): [ph1 tap 0 | ph3 tap 2] -> columns 1-2
 //   shift (1,0): [ph3 tap 1 | ph2 tap 0] -> columns 2-3
 //   shift (1,1): [ph3 tap 0]             -> column 2
-struct DgGroup { int col, ntl, s0, s1; };
+struct DgGroup { int col, ntl, idx; };            // idx: the group's position in the weight pack's 9-tile block (pack.cuh)
 __device__ __forceinline__ int dg_groups(int s) { return s == 0 ? 2 : 1; }
 __device__ __forceinline__ DgGroup dg_group(int s, int gi) {
-  if (s == 0) return gi == 0 ? DgGroup{0, 2, 0, 2} : DgGroup{2, 2, 8, 4};
-  if (s == 1) return DgGroup{1, 2, 1, 7};
-  if (s == 2) return DgGroup{2, 2, 6, 3};
-  return DgGroup{2, 1, 5, 5};
+  if (s == 0) return gi == 0 ? DgGroup{0, 2, 0} : DgGroup{2, 2, 1};
+  if (s == 1) return DgGroup{1, 2, 2};
+  if (s == 2) return DgGroup{2, 2, 3};
+  return DgGroup{2, 1, 4};
 }
 // phase `ph` is complete after shift `ph`; its accumulator column block
 __device__ __forceinline__ int dg_col_of_phase(int ph) { return ph == 2 ? 3 : ph == 3 ? 2 : ph; }
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
         const int m0 = mt * TILE_M;
         const int n0 = m0 >> (g.lHs + g.lWs);
         const int y0 = (m0 & (P - 1)) >> g.lWs;
-        // first weight tile of this n-tile in the pack (FPROP: NSUB consecutive pack n-tiles)
+        // first weight tile of this n-tile in the pack (FPROP: NSUB consecutive pack n-tiles; DGRAD: cpt blocks of 9 tiles)
         const uint8_t* wsrc = q.wtiles + (size_t)nt * (FAMILY == FAM_DGRAD ? 1 : NSUB) * q.wchunks * WTILE_BYTES;
         uint32_t wt = 0;
         for (int s = 0; s < NS; ++s) {
@@ -233,23 +233,21 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
                 if (++wslot_r == (uint32_t)nw) { wslot_r = 0; ++wround; }
               }
               const uint32_t w_dst = sW_u32 + wslot * W_SLOT;
-              int ntl;
-              const uint8_t *t0, *t1;
               if (FAMILY == FAM_DGRAD) {
+                // group pack: [hi of the group's tiles][lo of the group's tiles] is one contiguous region -> ONE copy
                 const DgGroup G = dg_group(s, gi);
-                ntl = G.ntl;
-                t0 = wsrc + (uint32_t)(G.s0 * q.cpt + c) * WTILE_BYTES;
-                t1 = wsrc + (uint32_t)(G.s1 * q.cpt + c) * WTILE_BYTES;
+                const uint32_t bytes = (uint32_t)G.ntl * WTILE_BYTES;
+                mbar_arrive_expect_tx(w_full(wslot), bytes);
+                bulk_copy_g2s(w_dst, wsrc + ((size_t)c * 9 + 2 * G.idx) * WTILE_BYTES, bytes, w_full(wslot));
               } else {
-                ntl = NSUB;
-                t0 = wsrc + (uint32_t)(s * q.cpt + c) * WTILE_BYTES;
-                t1 = t0 + (size_t)q.wchunks * WTILE_BYTES;
-              }
-              mbar_arrive_expect_tx(w_full(wslot), (uint32_t)ntl * WTILE_BYTES);
+                const uint8_t* t0 = wsrc + (uint32_t)(s * q.cpt + c) * WTILE_BYTES;
+                const uint8_t* t1 = t0 + (size_t)q.wchunks * WTILE_BYTES;
+                mbar_arrive_expect_tx(w_full(wslot), (uint32_t)NSUB * WTILE_BYTES);
 #pragma unroll
-              for (int pl = 0; pl < NSPLIT; ++pl) {
-                bulk_copy_g2s(w_dst + pl * GT * W_PLANE, t0 + pl * W_PLANE, W_PLANE, w_full(wslot));
-                if (GT == 2 && ntl == 2) bulk_copy_g2s(w_dst + pl * GT * W_PLANE + W_PLANE, t1 + pl * W_PLANE, W_PLANE, w_full(wslot));
+                for (int pl = 0; pl < NSPLIT; ++pl) {
+                  bulk_copy_g2s(w_dst + pl * GT * W_PLANE, t0 + pl * W_PLANE, W_PLANE, w_full(wslot));
+                  if (NSUB == 2) bulk_copy_g2s(w_dst + pl * GT * W_PLANE + W_PLANE, t1 + pl * W_PLANE, W_PLANE, w_full(wslot));
+                }
               }
             }
           }
@@ -301,17 +299,19 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
 #endif
               const uint64_t dw = desc_w0 + (uint64_t)((wslot * W_SLOT) >> 4);
               uint32_t acc = acc0, idesc = GT == 2 ? idesc2 : idesc1;
+              uint32_t lo_off = (GT * W_PLANE) >> 4;                   // lo plane behind the hi planes of the group's tiles
               if (FAMILY == FAM_DGRAD) {
                 const DgGroup G = dg_group(s, gi);
                 acc = acc0 + G.col * WT;
                 idesc = G.ntl == 2 ? idesc2 : idesc1;
+                lo_off = (uint32_t)(G.ntl * W_PLANE) >> 4;
               }
 #pragma unroll
               for (int kk = 0; kk < KC / 16; ++kk) {
                 const uint64_t ah = da + (uint64_t)(kk * 2), bh = dw + (uint64_t)(kk * 2);
                 umma_bf16(acc, ah, bh, idesc, !(fresh && kk == 0));
                 if (NSPLIT == 2) {
-                  umma_bf16(acc, ah, bh + (uint64_t)((GT * W_PLANE) >> 4), idesc, 1);
+                  umma_bf16(acc, ah, bh + (uint64_t)lo_off, idesc, 1);
                   umma_bf16(acc, ah + (uint64_t)(A_PLANE >> 4), bh, idesc, 1);
                 }
               }

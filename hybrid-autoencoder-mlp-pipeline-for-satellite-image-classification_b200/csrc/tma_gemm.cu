@@ -291,7 +291,18 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
             const int dy = (py && a == 0) ? 1 : 0, dx = (px && b == 0) ? 1 : 0;   // source = (y + dy, x + dx)
             tma_load_5d(a_dst, &q.amap[0], c0, dx, y0 + dy, n0, 0, full_bar(s));
           }
-          if (NSUB == 1) {
+          if (FAMILY == FAM_DGRAD) {
+            // group pack (pack.cuh): the planes of a tile are not adjacent -- one copy per plane and 64-row sub-tile
+            const int slot = kc_off / q.cpt + tap, c = it - tap * q.cpt;
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+              const uint8_t* blk = q.wtiles + ((size_t)(ntile * NSUB + sub) * q.cpt + c) * 9 * (NSPLIT * PK_PLANE);
+#pragma unroll
+              for (int pl = 0; pl < NSPLIT; ++pl)
+                bulk_copy_g2s(a_dst + A_BYTES + pl * B_PLANE + sub * PK_PLANE, blk + dg_pack_plane_offset(slot, pl, NSPLIT, PK_PLANE),
+                              PK_PLANE, full_bar(s));
+            }
+          } else if (NSUB == 1) {
             bulk_copy_g2s(a_dst + A_BYTES, wsrc + (size_t)it * B_BYTES, B_BYTES, full_bar(s));
           } else {
 #pragma unroll
@@ -481,7 +492,8 @@ extern "C" int ae_debug_set_trace(unsigned long long* buf) {
 // Tile (n_tile, chunk): [plane][NT rows][KC*2 bytes]; element (r, j) of a tile at
 //   r*ROWB + ((chunk16 ^ swz(r)) << 4) + (j & 7)*2,  chunk16 = j >> 3,
 //   swz(r) = r & 7 for 128-byte rows (SWIZZLE_128B), (r >> 1) & 3 for 64-byte rows (SWIZZLE_64B).
-// fwd  : n = cs, K order (tap, cb), KC = min(Cb, 64).   dgrad: n = cb, K order (phase-stacked tap slot, cs), KC = 64.
+// fwd  : n = cs, K order (tap, cb), KC = min(Cb, 64).   dgrad: n = cb, KC = 64, per (n-tile, K chunk) a block of the 9 tap
+//        tiles in the group order of pack.cuh (the tiles one N-stacked MMA reads are contiguous, plane by plane).
 // ---------------------------------------------------------------------------------------------
 static inline int nt_for(int n) { return n >= 64 ? 64 : 32; }
 static inline int kc_fwd(int Cb) { return Cb >= 64 ? 64 : 32; }
