@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 VARIANT = os.environ.get("AE_B200_BUILD_VARIANT", "")
 OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(HERE, "libae_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
-SOURCES = ["api.cu", "simt_gemm.cu", "thin.cu", "elementwise.cu", "head.cu", "mlp.cu", "tma_gemm.cu", "rowgemm2.cu", "engine.cu", "dp.cu", "augment.cu"]
+SOURCES = ["api.cu", "simt_gemm.cu", "thin.cu", "elementwise.cu", "head.cu", "mlp.cu", "tma_gemm.cu", "rowgemm2.cu", "dense_tc.cu", "engine.cu", "dp.cu", "augment.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + (["-DAE_TRACE"] if VARIANT == "trace" else [])

@@ -294,6 +294,13 @@ bool rowgemm2_supported(const RowGemm& p);   // shape + epilogue
 bool rowgemm2_preferred(const RowGemm& p);   // ... and measured to be the faster generation for this problem size
 int tma_rowgemm2(const RowGemm& p, const void* packed, int nsplit, cudaStream_t st);
 void rowgemm2_set_sm_reserve(int sms);       // SMs its one-CTA-per-SM grids leave to concurrently running collectives
+// dense_tc.cu: Linear over split-bf16 activation planes on tcgen05 (eval-mode encoder bottleneck)
+bool dense_tc_supported(int N, int K);
+size_t dense_tc_pack_bytes(int N, int K, int nsplit);
+int dense_tc_pack(const float* w, int N, int K, int permC, int permHW, int nsplit, void* pack, cudaStream_t st);
+int dense_tc_split(int M, int K);
+int dense_tc(const void* a_planes, const void* pack, int M, int N, int K, int nsplit, float* out_partial, size_t partial_bytes,
+             int* ksplit_out, cudaStream_t st);
 bool tma_wgrad_supported(const Geom& g);
 int tma_wgrad_slices(const Geom& g);
 size_t tma_wgrad_partial_bytes(const Geom& g);

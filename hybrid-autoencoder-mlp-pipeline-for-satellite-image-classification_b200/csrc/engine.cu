@@ -81,6 +81,7 @@ struct ae_engine {
   ae_engine_config_t cfg;
   int L, NC, Bmax;
   bool simt;
+  bool dense_tc = true;               // AE_B200_DENSE_TC=0: eval-mode Linear(4096, L) stays on the CUDA-core kernel
   int nsplit;             // bf16 operand split terms of the tcgen05 path
   Part part[AE_NUM_PARTS];
   MidLayer enc_mid[3];    // conv2..conv4
@@ -98,6 +99,7 @@ struct ae_engine {
   float *z = nullptr, *dz_dec = nullptr, *dz_head = nullptr, *dz_tot = nullptr;
   float *hid_pre = nullptr, *dhid = nullptr, *logits = nullptr, *dlogits = nullptr;
   // packs
+  void* encfc_tc = nullptr;           // tensor-core pack of the encoder's Linear(4096, L) (eval mode, dense_tc.cu)
   float *encfc_fwd = nullptr, *encfc_bwd = nullptr, *decfc_fwd = nullptr, *decfc_bwd = nullptr, *decfc_bias = nullptr;
   float *head_w1t = nullptr;
   // scratch
@@ -252,6 +254,7 @@ static size_t carve(ae_engine* e, char* base) {
   e->decfc_bwd = (float*)take((size_t)4096 * L * 4);
   e->decfc_bias = (float*)take(4096 * 4);
   e->head_w1t = (float*)take((size_t)128 * L * 4);
+  e->encfc_tc = (!e->simt && e->dense_tc && dense_tc_supported(L, 4096)) ? take(dense_tc_pack_bytes(L, 4096, e->nsplit)) : nullptr;
   // split-K / weight-gradient partial buffer
   size_t pb = 0;
   auto upd = [&](size_t v) { if (v > pb) pb = v; };
@@ -398,6 +401,7 @@ int ae_engine_create(const ae_engine_config_t* cfg, ae_engine_t** out) {
   e->cfg = *cfg;
   e->L = cfg->latent_dim; e->NC = cfg->num_classes; e->Bmax = cfg->max_batch;
   e->simt = cfg->backend == AE_BACKEND_SIMT;
+  { const char* v = getenv("AE_B200_DENSE_TC"); e->dense_tc = !(v && v[0] == '0'); }
   e->nsplit = cfg->precision == AE_PREC_FP32 ? 2 : 1;
   build_layouts(e);
   e->ws_need = carve(e, nullptr);
@@ -473,6 +477,7 @@ int ae_engine_pack_weights(ae_engine_t* e, int part, ae_stream_t stream) {
   if (part == AE_PART_ENC) {
     AE_TRY(pack_linear(p.P(16), L, 4096, 256, 16, 0, e->encfc_fwd, st));   // [4096 nhwc][L]
     AE_TRY(pack_linear(p.P(16), L, 4096, 256, 16, 1, e->encfc_bwd, st));   // [L][4096 nhwc]
+    if (e->encfc_tc) AE_TRY(dense_tc_pack(p.P(16), L, 4096, 256, 16, e->nsplit, e->encfc_tc, st));
   } else if (part == AE_PART_DEC) {
     AE_TRY(pack_linear(p.P(0), 4096, L, 256, 16, 2, e->decfc_fwd, st));    // [L][4096 nhwc]
     AE_TRY(pack_linear(p.P(0), 4096, L, 256, 16, 3, e->decfc_bwd, st));    // [4096 nhwc][L]
@@ -508,6 +513,11 @@ static int pack_all_parts(ae_engine* e, cudaStream_t st) {
   lin(D.P(0), 4096, L, 256, 16, 2, e->decfc_fwd);
   lin(D.P(0), 4096, L, 256, 16, 3, e->decfc_bwd);
   lin(H.P(0), 128, L, 0, 0, 0, e->head_w1t);
+  if (e->encfc_tc) {
+    PackJob& j = J.job[n++];
+    j.kind = PACK_DENSE_TC; j.src = E.P(16); j.dst = e->encfc_tc; j.dst2 = nullptr;
+    j.a = L; j.b = 4096; j.c = 256; j.d = 16; j.e = e->nsplit; j.total = L * 4096 / 8;
+  }
   {
     PackJob& j = J.job[n++];
     j.kind = PACK_PERMUTE; j.src = D.P(1); j.dst = e->decfc_bias; j.dst2 = nullptr;
@@ -556,9 +566,13 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
     r.epi.C = bout.C;
     r.out = e->y[i + 1]; r.splitK = 1; r.partial = nullptr;
     if (fused_eval) {
-      // the operand planes were written by the previous layer's epilogue; conv2 / conv3 write the next ones, conv4 stores
-      // fp32 for the dense layer (which applies BatchNorm + ReLU while it loads)
-      if (i < 2) { r.epi = bnrelu_split_epilogue(P.P(m.b), bout.bnc, bout.C, e->nsplit); r.out = (float*)e->ae_pl[i + 1]; }
+      // the operand planes were written by the previous layer's epilogue; conv2 / conv3 write the next ones; conv4 writes the
+      // planes of the tensor-core dense layer (h_pl is free during an encoder pass), or stores fp32 for the CUDA-core dense
+      // layer (which applies BatchNorm + ReLU while it loads)
+      if (i < 2 || e->encfc_tc) {
+        r.epi = bnrelu_split_epilogue(P.P(m.b), bout.bnc, bout.C, e->nsplit);
+        r.out = (float*)(i < 2 ? e->ae_pl[i + 1] : e->h_pl);
+      }
       r.A = split_operand(e->ae_pl[i], bin.C);
       AE_TRY(tma_rowgemm(r, m.pk_fwd, e->nsplit, st));
       continue;
@@ -572,7 +586,12 @@ int ae_encoder_forward(ae_engine_t* e, const float* x, int batch, int training, 
                        (int64_t)batch * bin.count_per_image * bin.C, m.pk_fwd, &job, st));
   }
   if (!fused_eval && e->simt) AE_TRY(run_bn_job(bn_fwd_job(P, 3, batch, training), st));
-  {  // Flatten + Linear(4096, L): split-K partials, fixed-order reduce (+bias)
+  if (fused_eval && e->encfc_tc) {   // Flatten + Linear(4096, L) on tcgen05 over conv4's planes
+    int ks = 1;
+    AE_TRY(dense_tc(e->h_pl, e->encfc_tc, batch, e->L, 4096, e->nsplit, e->partial, e->partial_bytes, &ks, st));
+    AE_TRY(reduce_partials(e->partial, ks, (int64_t)batch * e->L, P.P(17), e->L, nullptr, e->z, st));
+    if (z && z != e->z) AE_CUDA(cudaMemcpyAsync(z, e->z, (size_t)batch * e->L * 4, cudaMemcpyDeviceToDevice, st));
+  } else {  // Flatten + Linear(4096, L): split-K partials, fixed-order reduce (+bias)
     RowGemm r{};
     r.family = FAM_DENSE; r.M = batch; r.N = e->L; r.K = 4096;
     r.A = bnrelu_operand(e->y[3], P.bn[3].bnc, 256);

@@ -110,19 +110,44 @@ __device__ __forceinline__ void pack_linear_elem(int idx, const float* __restric
   }
 }
 
+// Tensor-core pack of a Linear weight w [N][K] (torch) whose INPUT is NHWC-flattened (dense_tc.cu): per 64-deep K chunk one
+// SWIZZLE_128B tile [hi plane][lo plane] of N rows x 128 bytes; K index k of the pack is the reference's perm(k).
+// idx8 in [0, N*K/8): 8 consecutive K elements = one 16-byte chunk of a row.
+__device__ __forceinline__ void pack_dense_tc_chunk(int idx8, const float* __restrict__ w, int N, int K, int permC, int permHW,
+                                                    int nsplit, uint8_t* __restrict__ dst) {
+  const int n = idx8 / (K / 8), k = (idx8 - n * (K / 8)) * 8;
+  const int chunk = k / 64, j = k - chunk * 64;
+  float v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int ku = k + u;
+    v[u] = w[(size_t)n * K + (permC > 0 ? (ku % permC) * permHW + ku / permC : ku)];
+  }
+  const size_t plane = (size_t)N * 128;
+  const size_t off = (size_t)chunk * nsplit * plane + (size_t)n * 128 + (size_t)(((j >> 3) ^ (n & 7)) << 4);
+  __nv_bfloat162 h[4], l[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    h[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+    l[u] = __floats2bfloat162_rn(v[2 * u] - __bfloat162float(h[u].x), v[2 * u + 1] - __bfloat162float(h[u].y));
+  }
+  *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(h);
+  if (nsplit == 2) *reinterpret_cast<uint4*>(dst + off + plane) = *reinterpret_cast<const uint4*>(l);
+}
+
 __device__ __forceinline__ void permute_elem(int i, const float* __restrict__ src, int permC, int permHW, float* __restrict__ dst) {
   dst[i] = src[(i % permC) * permHW + i / permC];
 }
 
 // A batch of re-layout jobs executed by ONE launch (k_pack_all): after every optimizer step the engine re-derives
 // the six conv weight packs and the dense-layer packs.
-enum { PACK_CONV = 0, PACK_LINEAR = 1, PACK_PERMUTE = 2 };
+enum { PACK_CONV = 0, PACK_LINEAR = 1, PACK_PERMUTE = 2, PACK_DENSE_TC = 3 };
 struct PackJob {
   int kind;
   const float* src;
   void* dst;
   void* dst2;
-  int a, b, c, d, e;        // CONV: Cs, Cb, nsplit.  LINEAR: N, K, permC, permHW, lkind.  PERMUTE: n, permC, permHW
+  int a, b, c, d, e;        // CONV: Cs, Cb, nsplit.  LINEAR: N, K, permC, permHW, lkind.  PERMUTE: n, permC, permHW.  DENSE_TC: N, K, permC, permHW, nsplit
   int total;                // work items: 8-element chunks (CONV) or elements
   int first_block;          // first block of this job in the fused launch
 };

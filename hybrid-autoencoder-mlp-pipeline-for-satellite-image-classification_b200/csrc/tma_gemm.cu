@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(256) k_pack_all(const __grid_constant__ PackJo
   for (int idx = ((int)blockIdx.x - J.first_block) * blockDim.x + threadIdx.x; idx < J.total; idx += nblk * blockDim.x) {
     if (J.kind == PACK_CONV) pack_conv_chunk(idx, J.src, J.a, J.b, J.c, (uint8_t*)J.dst, (uint8_t*)J.dst2);
     else if (J.kind == PACK_LINEAR) pack_linear_elem(idx, J.src, J.a, J.b, J.c, J.d, J.e, (float*)J.dst);
+    else if (J.kind == PACK_DENSE_TC) pack_dense_tc_chunk(idx, J.src, J.a, J.b, J.c, J.d, J.e, (uint8_t*)J.dst);
     else permute_elem(idx, J.src, J.b, J.c, (float*)J.dst);
   }
 }
