@@ -4,12 +4,16 @@
 //   both layers store their weight as [32][3][3][3] = [c32][c3][ky][kx].
 //
 // All kernels are persistent and work on tiles of 4 wide rows x 32 wide columns (128 wide pixels = 8 thin rows) of
-// one image.  The raw thin rows and the raw wide tile of the NEXT tile are fetched by TMA bulk copies
-// (cp.async.bulk + mbarrier, double buffered) while the current tile is computed; one in-place pass applies the
-// operand transform once per element.  128 threads; in the gather every thread owns 8 consecutive wide pixels x 4
+// one image.  The raw thin rows of the NEXT tile arrive with ONE TMA tensor load per source (box [3 channels][9 rows][72
+// columns] of the NCHW image starting at column -4, row 8*tr-1: the zero padding of the convolution is the tensor map's
+// out-of-bounds fill) and its raw wide tile with one bulk copy (mbarrier, double buffered) while the current tile is
+// computed; one in-place pass applies the operand transform once per element.  (Round 2: the 27 row-by-row bulk copies
+// this replaced kept warp 0 issuing for ~2.7 k cycles per tile while the other warps waited at the barrier -- ncu: 35 % of
+// all stall samples.)  128 threads; in the gather every thread owns 8 consecutive wide pixels x 4
 // output channels (one 16-byte weight load and 5/3 patch loads feed 32 FMAs: the kernel is bound by FMA issue, not by
 // the shared-memory pipe).
 #include "thin_common.cuh"
+#include "tma_host.cuh"
 
 namespace ae {
 
@@ -21,7 +25,9 @@ namespace ae {
 // ---------------------------------------------------------------------------------------------
 template <bool GATHER, bool WGRAD>
 __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wide, const float* __restrict__ w, Epilogue e,
-                                                     float* __restrict__ out, float* __restrict__ partial, int batch) {
+                                                     float* __restrict__ out, float* __restrict__ partial, int batch,
+                                                     const __grid_constant__ CUtensorMap xmap,
+                                                     const __grid_constant__ CUtensorMap xmap2) {
   extern __shared__ __align__(128) float smem_f[];
   const ThinStage L = thin_stage_layout(thin.mode, wide.mode, WGRAD);
   float* stage0 = smem_f;                               // two stages of L.floats floats
@@ -35,6 +41,8 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
   const uint32_t bar0 = smem_u32(&bars[0]);
 
   if (tid == 0) {
+    tma_prefetch_desc(&xmap);
+    if (thin.mode != AE_OP_RAW) tma_prefetch_desc(&xmap2);
     mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
     fence_barrier_init();
   }
@@ -56,10 +64,6 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
     const int rows_relu[4] = {AE_BNC_SCALE, AE_BNC_SHIFT, AE_BNC_SCALE, AE_BNC_SHIFT};
     const int rows_bwd[4] = {AE_BNC_A, AE_BNC_B, AE_BNC_C, AE_BNC_MEAN};
     wbn[tid] = __ldg(wide.bnc + (wide.mode == AE_OP_BNRELU ? rows_relu[tid >> 5] : rows_bwd[tid >> 5]) * WC + lane);
-  }
-  for (int i = tid; i < 2 * 3 * XS_ROWS; i += TT_THREADS) {   // left zero padding of both stages, never overwritten
-    const int st = i / (3 * XS_ROWS), r = i - st * 3 * XS_ROWS;
-    stage0[st * L.floats + r * XS_PITCH + 3] = 0.f;
   }
   // GATHER: this thread's 8 wide pixels (tile row g_r, columns g_x0 .. g_x0+7) and 4 channels (g_c0 .. g_c0+3)
   const int g_c0 = (tid & 7) * 4, g_r = tid >> 5, g_x0 = ((tid >> 3) & 3) * 8;
@@ -89,18 +93,13 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
     const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;
     const uint32_t bar = bar0 + 8u * st;
     float* base = stage0 + st * L.floats;
-    const int r_first = tr == 0 ? 1 : 0;                    // thin row -1 does not exist: zero-filled by the transform pass
     const int nsrc = thin.mode != AE_OP_RAW ? 2 : 1;
-    uint32_t bytes = (uint32_t)(3 * (XS_ROWS - r_first) * TW * 4 * nsrc);
+    uint32_t bytes = (uint32_t)(XS_BYTES * nsrc);           // a box always delivers all its bytes (zeros where out of bounds)
     if (WGRAD) bytes += WT_BYTES * (wide.mode == AE_OP_BNBWD ? 2 : 1);
     mbar_arrive_expect_tx(bar, bytes);
-    for (int c3 = 0; c3 < 3; ++c3)
-      for (int r = r_first; r < XS_ROWS; ++r) {
-        const size_t off = (((size_t)n * 3 + c3) * TH + (2 * TILE_ROWS * tr - 1 + r)) * TW;
-        const int so = (c3 * XS_ROWS + r) * XS_PITCH + 4;
-        bulk_copy_g2s(smem_u32(base + so), thin.src + off, TW * 4, bar);
-        if (nsrc == 2) bulk_copy_g2s(smem_u32(base + L.xs2 + so), thin.src2 + off, TW * 4, bar);
-      }
+    // thin rows 8*tr-1 .. 8*tr+7, columns -4 .. 67: column c lands at index c + 4 of its XS_PITCH-wide row
+    tma_load_4d(smem_u32(base), &xmap, -4, 2 * TILE_ROWS * tr - 1, 0, n, bar);
+    if (nsrc == 2) tma_load_4d(smem_u32(base + L.xs2), &xmap2, -4, 2 * TILE_ROWS * tr - 1, 0, n, bar);
     if (WGRAD) {
       const size_t m0 = ((size_t)n * WH + tr * TILE_ROWS) * WW;
       bulk_copy_g2s(smem_u32(base + L.wide), wide.src + m0 * WC, WT_BYTES, bar);
@@ -128,21 +127,18 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
     }
     mbar_wait(bar0 + 8u * st, (it >> 1) & 1);
     // ---- transform pass (in place, once per element) ----
-    if (thin.mode != AE_OP_RAW || tr == 0 || WGRAD) {
+    if (thin.mode != AE_OP_RAW || WGRAD) {
       for (int i = tid; i < 3 * XS_ROWS * 16; i += TT_THREADS) {
         const int q = i & 15, r = (i >> 4) % XS_ROWS, c3 = i / (16 * XS_ROWS);
         float* px = xs + (c3 * XS_ROWS + r) * XS_PITCH + 4 + q * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r > 0 || tr > 0) {
-          v = *reinterpret_cast<const float4*>(px);
-          if (thin.mode != AE_OP_RAW) {
-            const float4 sg = *reinterpret_cast<const float4*>(px + L.xs2);
-            v.x = thin_transform(thin, v.x, sg.x); v.y = thin_transform(thin, v.y, sg.y);
-            v.z = thin_transform(thin, v.z, sg.z); v.w = thin_transform(thin, v.w, sg.w);
-          }
-          if (WGRAD && r >= 1) bsum[c3 == 0 ? 0 : (c3 == 1 ? 1 : 2)] += (v.x + v.y) + (v.z + v.w);
+        float4 v = *reinterpret_cast<const float4*>(px);    // thin row -1 (r == 0 of an image's first tile) arrived as zeros
+        if (thin.mode != AE_OP_RAW) {
+          const float4 sg = *reinterpret_cast<const float4*>(px + L.xs2);
+          v.x = thin_transform(thin, v.x, sg.x); v.y = thin_transform(thin, v.y, sg.y);
+          v.z = thin_transform(thin, v.z, sg.z); v.w = thin_transform(thin, v.w, sg.w);
+          *reinterpret_cast<float4*>(px) = v;
         }
-        if (thin.mode != AE_OP_RAW || (r == 0 && tr == 0)) *reinterpret_cast<float4*>(px) = v;
+        if (WGRAD && r >= 1) bsum[c3 == 0 ? 0 : (c3 == 1 ? 1 : 2)] += (v.x + v.y) + (v.z + v.w);
       }
     }
     if (WGRAD && wide.mode != AE_OP_RAW) {
@@ -190,10 +186,8 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
 #pragma unroll
             for (int px = 0; px < 8; ++px) {
               const float xa = p[2 * px + 3 + kx];
-              acc[px][0] = fmaf(xa, wv.x, acc[px][0]);
-              acc[px][1] = fmaf(xa, wv.y, acc[px][1]);
-              acc[px][2] = fmaf(xa, wv.z, acc[px][2]);
-              acc[px][3] = fmaf(xa, wv.w, acc[px][3]);
+              fma2(acc[px][0], acc[px][1], xa, wv.x, wv.y);
+              fma2(acc[px][2], acc[px][3], xa, wv.z, wv.w);
             }
           }
         }
@@ -262,10 +256,8 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
           const float t = pb[koff[j]];
-          wacc[0][j] = fmaf(a4.x, t, wacc[0][j]);
-          wacc[1][j] = fmaf(a4.y, t, wacc[1][j]);
-          wacc[2][j] = fmaf(a4.z, t, wacc[2][j]);
-          wacc[3][j] = fmaf(a4.w, t, wacc[3][j]);
+          fma2(wacc[0][j], wacc[1][j], t, a4.x, a4.y);
+          fma2(wacc[2][j], wacc[3][j], t, a4.z, a4.w);
         }
       }
     }
@@ -362,6 +354,21 @@ static int resident_blocks(Kernel kernel, size_t smem, int batch, int* blocks) {
   return 0;
 }
 
+// [batch][3][64][64] fp32 image as a 4-d tensor map; box = (XS_PITCH columns, XS_ROWS rows, 3 channels, 1 image)
+static int encode_image_map(CUtensorMap* map, const float* img, int batch) {
+  EncodeTiledFn fn = encode_fn();
+  AE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[4] = {(cuuint64_t)TW, (cuuint64_t)TH, 3, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)TW * 4, (cuuint64_t)TH * TW * 4, (cuuint64_t)3 * TH * TW * 4};
+  cuuint32_t box[4] = {(cuuint32_t)XS_PITCH, (cuuint32_t)XS_ROWS, 3, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(img), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AE_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (image) failed with CUresult %d (batch %d)", (int)r, batch);
+  return 0;
+}
+
 template <bool GATHER, bool WGRAD>
 static int launch_thin(const Operand& thin, const Operand& wide, const float* w, const Epilogue& e, float* out,
                        float* partial, int batch, cudaStream_t st, int* blocks_out = nullptr) {
@@ -378,7 +385,11 @@ static int launch_thin(const Operand& thin, const Operand& wide, const float* w,
   int blocks = 0;
   AE_TRY(resident_blocks(k_thin<GATHER, WGRAD>, smem, batch, &blocks));
   if (blocks_out) *blocks_out = blocks;
-  k_thin<GATHER, WGRAD><<<blocks, TT_THREADS, smem, st>>>(thin, wide, w, e, out, partial, batch);
+  CUtensorMap xmap, xmap2;
+  AE_TRY(encode_image_map(&xmap, thin.src, batch));
+  if (thin.mode != AE_OP_RAW) AE_TRY(encode_image_map(&xmap2, thin.src2, batch));
+  else xmap2 = xmap;
+  k_thin<GATHER, WGRAD><<<blocks, TT_THREADS, smem, st>>>(thin, wide, w, e, out, partial, batch, xmap, xmap2);
   AE_LAUNCH_CHECK();
   return 0;
 }

@@ -10,13 +10,19 @@ static constexpr int TILE_ROWS = 4;                    // wide rows per tile
 static constexpr int TILES_PER_IMAGE = WH / TILE_ROWS; // 8
 static constexpr int XS_ROWS = 2 * TILE_ROWS + 1;      // thin rows 8*tr-1 .. 8*tr+7
 static constexpr int XS_PITCH = 72;                    // thin column c at index c + 4; index 3 = left zero padding
-static constexpr int XS_FLOATS = 3 * XS_ROWS * XS_PITCH;
+static constexpr int XS_FLOATS = (3 * XS_ROWS * XS_PITCH + 31) / 32 * 32;   // one TMA box [3][XS_ROWS][XS_PITCH], padded to 128 bytes
 static constexpr int TW_PART = 868;                    // 864 weights + 3 thin-bias sums + 1 pad
 
 __device__ __forceinline__ float thin_transform(const Operand& op, float a, float s) {
   if (op.mode == AE_OP_RAW) return a;
   const float up = (op.scalar != 0.f) ? op.scalar * (s - a) : a;   // fused MSE gradient, or a given upstream gradient
   return up * s * (1.f - s);                                       // AE_OP_SIGMOID_BWD
+}
+
+// (d0, d1) += a * (b0, b1): one packed fp32 FMA (FFMA2, scalar operand broadcast); each half rounds like fmaf
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1) {
+  const float2 r = __ffma2_rn(make_float2(a, a), make_float2(b0, b1), make_float2(d0, d1));
+  d0 = r.x; d1 = r.y;
 }
 
 // lane l ends with the sum over the warp's 32 lanes of element v[l]  (31 shuffles)
@@ -34,7 +40,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-static constexpr int XS_BYTES = XS_FLOATS * 4;
+static constexpr int XS_BYTES = 3 * XS_ROWS * XS_PITCH * 4;   // bytes one image box delivers
 static constexpr int WT_FLOATS = 128 * 32;             // one wide tile
 static constexpr int WT_BYTES = WT_FLOATS * 4;
 

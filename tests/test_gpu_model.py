@@ -490,6 +490,27 @@ def test_eval_encoder_walks_large_batches_in_chunks(monkeypatch):
     assert gu.rel(z_chunked, ref) <= 1e-4
 
 
+@pytest.mark.parametrize("latent,batch", [(16, 5), (48, 130), (64, 300), (128, 129), (256, 257)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_eval_bottleneck_on_tensor_cores_matches_oracle_and_cuda_core_path(latent, batch, prec, monkeypatch):
+    """Eval-mode Flatten + Linear(4096, latent) (NB:520-521) runs on tcgen05 over the planes conv4's epilogue emits
+    (dense_tc.cu): every latent width the kernel accepts, ragged 128-row tiles, against the oracle and against the CUDA-core
+    kernel (AE_B200_DENSE_TC=0, read when the engine is created)."""
+    x = seeded.seeded_images(batch, 31 + latent)
+    zs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AE_B200_DENSE_TC", flag)
+        ae = ae_b200.SupervisedAutoencoder(latent, precision=prec, backend="tc").to(gu.dev())
+        st = gu.load_ae(ae, 17, latent)
+        ae.enc.eval()
+        with torch.no_grad():
+            zs[flag] = ae.enc(x.to(gu.dev())).clone()
+    torch.cuda.synchronize()
+    ref = tp.encoder_forward(st, x, False)
+    assert gu.rel(zs["1"], ref) <= gu.TOL[prec]
+    assert gu.rel(zs["1"], zs["0"]) <= gu.TOL[prec]
+
+
 def test_backward_after_another_forward_raises():
     """The activations of a forward live in the engine's workspace: a backward whose forward was overwritten by a later
     forward must raise instead of silently using the newer activations (gradient accumulation over two forwards, retained
