@@ -12,6 +12,8 @@
 // all stall samples.)  128 threads; in the gather every thread owns 8 consecutive wide pixels x 4
 // output channels (one 16-byte weight load and 5/3 patch loads feed 32 FMAs: the kernel is bound by FMA issue, not by
 // the shared-memory pipe).
+#include <cstring>
+
 #include "thin_common.cuh"
 #include "tma_host.cuh"
 
@@ -354,13 +356,13 @@ static int resident_blocks(Kernel kernel, size_t smem, int batch, int* blocks) {
   return 0;
 }
 
-// [batch][3][64][64] fp32 image as a 4-d tensor map; box = (XS_PITCH columns, XS_ROWS rows, 3 channels, 1 image)
-static int encode_image_map(CUtensorMap* map, const float* img, int batch) {
+// [batch][3][64][64] fp32 image as a 4-d tensor map; box = (box_cols columns, box_rows rows, 3 channels, 1 image)
+static int encode_image_map(CUtensorMap* map, const float* img, int batch, int box_cols = XS_PITCH, int box_rows = XS_ROWS) {
   EncodeTiledFn fn = encode_fn();
   AE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[4] = {(cuuint64_t)TW, (cuuint64_t)TH, 3, (cuuint64_t)batch};
   cuuint64_t strides[3] = {(cuuint64_t)TW * 4, (cuuint64_t)TH * TW * 4, (cuuint64_t)3 * TH * TW * 4};
-  cuuint32_t box[4] = {(cuuint32_t)XS_PITCH, (cuuint32_t)XS_ROWS, 3, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 3, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(img), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -459,18 +461,20 @@ static constexpr int AS_ROWS = TILE_ROWS + 1, AS_COLS = WW + 1;
 __global__ void __launch_bounds__(TT_THREADS, 4) k_thin_scatter_sigmoid(Operand wide, const float* __restrict__ w,
                                                                      const float* __restrict__ bias, float* __restrict__ x_hat,
                                                                      const float* __restrict__ x, double* __restrict__ sse,
-                                                                     int batch) {
+                                                                     int batch, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) float smem_f[];
   float* raw = smem_f;                                  // [AS_ROWS][32][32]: the tile's wide rows + the halo row, one bulk copy
   float* as = raw + AS_ROWS * WW * WC;                  // [AS_ROWS][AS_COLS][32] transformed, 16-byte chunk c of pixel p at c ^ (p & 7)
   float* Wsm = as + AS_ROWS * AS_COLS * 32;             // [9 taps][3 co][32 ci]
   float* sbn = Wsm + 27 * 32;                           // [2][32] scale, shift of the wide operand
-  __shared__ __align__(8) uint64_t bar_raw;
+  float* xt = sbn + 64;                                 // [3][8][64]: the tile's rows of the target image (one TMA box)
+  __shared__ __align__(8) uint64_t bar_raw, bar_x;
   __shared__ float red[TT_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t bar = smem_u32(&bar_raw);
+  const uint32_t bar = smem_u32(&bar_raw), barx = smem_u32(&bar_x);
   if (tid == 0) {
-    mbar_init(bar, 1);
+    if (x) tma_prefetch_desc(&tmap);
+    mbar_init(bar, 1); mbar_init(barx, 1);
     fence_barrier_init();
   }
   for (int o = tid; o < 27 * 32; o += TT_THREADS) {     // o = (tap*3 + co)*32 + ci  <-  w[ci][co][tap]
@@ -512,9 +516,13 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin_scatter_sigmoid(Operand 
       *reinterpret_cast<float4*>(as + p * 32 + ((q ^ (p & 7)) << 2)) = v;
     }
     __syncthreads();                                    // `as` complete, `raw` consumed
-    if (tid == 0 && tile + (int)gridDim.x < tiles) {    // the next tile's rows arrive while this one is computed
+    if (tid == 0) {
       fence_proxy_async();
-      issue(tile + gridDim.x);
+      if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x);   // the next tile's rows arrive while this one is computed
+      if (x) {                                          // ... and so do this tile's rows of the target image (squared error)
+        mbar_arrive_expect_tx(barx, 3 * 2 * TILE_ROWS * TW * 4);
+        tma_load_4d(smem_u32(xt), &tmap, 0, 2 * TILE_ROWS * tr, 0, n, barx);
+      }
     }
     // Thread (warp = tile row, strip = lane >> 2, ciq = lane & 3): the 2x2x3 output quads of the strip's 4 wide pixels,
     // summed over input channels {ciq*4 .. +3} and {16 + ciq*4 .. +3}; one weight load feeds 16 FMAs.  A two-stage
@@ -581,6 +589,7 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin_scatter_sigmoid(Operand 
       }
     }
     const int ty0 = 2 * (tr * TILE_ROWS + warp);        // first of this thread's two thin rows; its wide column is x0 + ciq
+    if (x) mbar_wait(barx, it & 1);
 #pragma unroll
     for (int co = 0; co < 3; ++co) {
       const float b = co == 0 ? b0 : (co == 1 ? b1 : b2);
@@ -591,7 +600,7 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin_scatter_sigmoid(Operand 
         const float s1 = 1.f / (1.f + expf(-(r2[(py * 2 + 1) * 3 + co] + b)));
         *reinterpret_cast<float2*>(x_hat + o) = make_float2(s0, s1);
         if (x) {
-          const float2 t = __ldg(reinterpret_cast<const float2*>(x + o));
+          const float2 t = *reinterpret_cast<const float2*>(xt + (co * 2 * TILE_ROWS + 2 * warp + py) * TW + 2 * (x0 + ciq));
           err += (s0 - t.x) * (s0 - t.x) + (s1 - t.y) * (s1 - t.y);
         }
       }
@@ -610,7 +619,7 @@ int thin_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* b
                              double* sse, int batch, cudaStream_t st) {
   AE_CHECK(wide.mode == AE_OP_RAW || wide.mode == AE_OP_BNRELU, "thin_scatter: wide operand mode %d not supported", wide.mode);
   AE_CHECK(((uintptr_t)wide.src & 15) == 0, "thin_scatter: the wide tensor must be 16-byte aligned");
-  const size_t smem = sizeof(float) * (AS_ROWS * WW * WC + AS_ROWS * AS_COLS * 32 + 27 * 32 + 64);
+  const size_t smem = sizeof(float) * (AS_ROWS * WW * WC + AS_ROWS * AS_COLS * 32 + 27 * 32 + 64 + 3 * 2 * TILE_ROWS * TW);
   static bool attr_done = false;
   if (!attr_done) {
     AE_CUDA(cudaFuncSetAttribute(k_thin_scatter_sigmoid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -618,7 +627,14 @@ int thin_scatter_sigmoid_fwd(const Operand& wide, const float* w, const float* b
   }
   int blocks = 0;
   AE_TRY(resident_blocks(k_thin_scatter_sigmoid, smem, batch, &blocks));
-  k_thin_scatter_sigmoid<<<blocks, TT_THREADS, smem, st>>>(wide, w, bias, x_hat, x, sse, batch);
+  CUtensorMap tmap;
+  if (x) {
+    AE_CHECK(((uintptr_t)x & 15) == 0, "thin_scatter: the target image must be 16-byte aligned");
+    AE_TRY(encode_image_map(&tmap, x, batch, TW, 2 * TILE_ROWS));
+  } else {
+    memset(&tmap, 0, sizeof(tmap));
+  }
+  k_thin_scatter_sigmoid<<<blocks, TT_THREADS, smem, st>>>(wide, w, bias, x_hat, x, sse, batch, tmap);
   AE_LAUNCH_CHECK();
   return 0;
 }

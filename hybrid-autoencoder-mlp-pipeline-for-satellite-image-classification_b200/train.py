@@ -6,6 +6,7 @@ copies the batch into those buffers and replays the graph.  Equivalent to the lo
 from __future__ import annotations
 
 import ctypes as C
+import gc
 
 import torch
 
@@ -223,10 +224,14 @@ class MLPTrainStep:
                                         seed, ptr(self.seed_dev), float(clf.net[3].p), batch, d, c, ptr(self.logits), ptr(self.loss),
                                         ptr(self.correct), st.ws_ptr, st.ws_bytes, C.byref(cfg), ptr(ast["m"]), ptr(ast["v"]),
                                         ptr(ast["step"]), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        # Collect garbage BEFORE the capture and capture in relaxed mode: a cyclic-GC pass that happens to run inside the capture
+        # window may finalise an old TrainStep, whose close() synchronises its own stream -- in the default (global) mode that
+        # unrelated call invalidates this capture.
+        gc.collect()
         with torch.cuda.stream(stream):
             # (no warm-up launch: it would be a real optimizer step; the kernels allocate nothing)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=stream):
+            with torch.cuda.graph(self.graph, stream=stream, capture_error_mode="relaxed"):
                 call()
         torch.cuda.current_stream(dev).wait_stream(stream)
         for p_, g in zip(st.flat.params, st.flat.grad_views(st.flat.grad)):

@@ -98,6 +98,9 @@ def run(batch):
             ("conv1 weight gradient", conv1_wgrad, img_b + 2 * wide_b, fma),
             ("convT(32,3) forward + sigmoid + SSE", convt_fwd, 2 * img_b + wide_b, fma),
             ("convT(32,3) fused backward", convt_bwd, 2 * img_b + 3 * wide_b, 2 * fma)]
+    only = os.environ.get("THIN_ONLY")                      # e.g. THIN_ONLY=3 profiles one row under ncu
+    if only:
+        rows = [rows[int(i)] for i in only.split(",")]
     for name, fn, nbytes, nfma in rows:
         us = timed(fn, nrot)
         print(f"batch {batch:5d}  {name:40s} {us:8.2f} us   {nbytes / us / 1e3:7.1f} GB/s   {nfma / us / 1e6:6.2f} TFMA/s")
