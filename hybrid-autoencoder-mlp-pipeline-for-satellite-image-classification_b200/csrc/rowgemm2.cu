@@ -31,7 +31,7 @@ namespace ae {
 
 static constexpr int R2_THREADS = 320;   // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2..9: epilogue
 static constexpr int R2_MAXRING = 12;
-static constexpr int R2_BLOCK_BYTES = 4096;        // one staged 32 x 32 fp32 block; 8 output blocks (+ 8 y blocks: ReLU backward)
+static constexpr int R2_BLOCK_BYTES = 4096;        // one staged 32 x 32 fp32 block; 8 output blocks (+ 2 x 8 y blocks: ReLU backward)
 
 #ifdef AE_TRACE
 __device__ unsigned long long* g_trace2 = nullptr;
@@ -58,6 +58,7 @@ struct alignas(64) TmaRow2 {
   int cpt;                  // K chunks per tap (C / KC)
   int wchunks;              // K chunks per n-tile in the weight pack
   int na, nw;               // ring slots
+  int ny;                   // forward-activation blocks per epilogue warp (ReLU backward): 2 when shared memory allows
   int resident;             // the (single) n-tile's weight groups are loaded once and stay in the ring
   int bx, by, bn;           // pixel box of one 128-row tile
   BnJob job;                // kind != BN_JOB_NONE: coefficient job of epi.stats, run by the last CTA to finish
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[4 * R2_MAXRING + 18];
+  __shared__ __align__(8) uint64_t bars[4 * R2_MAXRING + 26];
   __shared__ uint32_t tmem_slot;
   __shared__ float sStat[2][MAXN];
   __shared__ __align__(16) float sCoef[MAXN][4];
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
   auto w_empty = [&](int s) { return bar0 + 8u * (3 * R2_MAXRING + s); };
   auto tfull = [&](int b, int ph) { return bar0 + 8u * (4 * R2_MAXRING + b * 4 + ph); };
   auto tempty = [&](int b) { return bar0 + 8u * (4 * R2_MAXRING + 8 + b); };
-  auto ybar = [&](int w) { return bar0 + 8u * (4 * R2_MAXRING + 10 + w); };
+  auto ybar = [&](int w) { return bar0 + 8u * (4 * R2_MAXRING + 10 + w); };   // w in [0, 16): warp + 8 * y slot
 
   if (tid == 0) {
     if (FAMILY == FAM_FPROP) {
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
       for (int ph = 0; ph < 4; ++ph) mbar_init(tfull(b, ph), 1);
       mbar_init(tempty(b), EPI_WARPS);
     }
-    for (int w = 0; w < 8; ++w) mbar_init(ybar(w), 1);
+    for (int w = 0; w < 16; ++w) mbar_init(ybar(w), 1);
     fence_barrier_init();
   }
   for (int c = tid; c < MAXN; c += R2_THREADS) { sStat[0][c] = 0.f; sStat[1][c] = 0.f; }
@@ -341,9 +342,10 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
     const bool relubwd = e.mode == AE_EPI_RELUBWD_STATS;
     const bool do_stats = e.mode != AE_EPI_STORE && e.stats != nullptr;
     uint8_t* Oreg = sStage + (size_t)ew * R2_BLOCK_BYTES;
-    uint8_t* Yreg = sStage + (size_t)(8 + ew) * R2_BLOCK_BYTES;        // only carved for the ReLU-backward epilogue
-    const uint32_t y_u32 = smem_u32(Yreg), o_u32 = smem_u32(Oreg);
-    const uint32_t yb = ybar(ew);
+    // forward activations of the ReLU-backward epilogue: two blocks per warp (only carved for that epilogue), so that the
+    // load of the warp's next unit is in flight while the current one is processed
+    uint8_t* const Yreg0 = sStage + (size_t)(8 + ew) * R2_BLOCK_BYTES;
+    const uint32_t o_u32 = smem_u32(Oreg);
     const int P = g.Hs * g.Ws;
     if (h < (UNITS >= 2 ? 2 : 1)) {
       // the warp's 32-row block of tile `tile`: pixel coordinates of its first row
@@ -355,17 +357,26 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
         y0 = (mrow & (P - 1)) >> g.lWs;
         n0 = mrow >> (g.lHs + g.lWs);
       };
-      auto issue_y = [&](int tile, int u) {                 // lane 0
+      auto issue_y = [&](int tile, int u, uint32_t slot) {  // lane 0
         int nt, x0, y0, n0, mrow;
         block_origin(tile, nt, x0, y0, n0, mrow);
         const int ph = u / CB, cb = u - ph * CB;
+        const uint32_t yb = ybar(ew + 8 * slot);
         mbar_arrive_expect_tx(yb, R2_BLOCK_BYTES);
-        tma_load_4d(y_u32, &q.ymap[ph], nt * PW + cb * 32, x0, y0, n0, yb);
+        tma_load_4d(smem_u32(Yreg0) + slot * 8 * R2_BLOCK_BYTES, &q.ymap[ph], nt * PW + cb * 32, x0, y0, n0, yb);
+      };
+      // the warp's unit sequence: (tile, u) -> (tile, u + 2) ... -> (tile + gridDim.x, h) ...
+      auto next_unit = [&](int& tile, int& u) {
+        u += 2;
+        if (u >= UNITS) { tile += gridDim.x; u = h; }
       };
       if (relubwd && lane == 0) {
 #pragma unroll
         for (int i = 0; i < NPH; ++i) tma_prefetch_desc(&q.ymap[i]);
-        issue_y(blockIdx.x, h);
+        int t0 = blockIdx.x, u0 = h;
+        if (t0 < num_tiles) issue_y(t0, u0, 0);
+        next_unit(t0, u0);
+        if (q.ny == 2 && t0 < num_tiles) issue_y(t0, u0, 1);
       }
       uint32_t ycount = 0, ti = 0;
       const int swz = lane & 7;
@@ -378,7 +389,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
           const int ph = u / CB, cb = u - ph * CB;         // phases in the order they complete
           const int n = nt * PW + cb * 32;                 // first output channel of the block
           const uint32_t col = (FAMILY == FAM_DGRAD ? dg_col_of_phase(ph) * WT : 0) + cb * 32;
-          if (relubwd) mbar_wait(yb, ycount & 1);
+          const uint32_t yslot = q.ny == 2 ? (ycount & 1) : 0;
+          const uint8_t* Yreg = Yreg0 + (size_t)yslot * 8 * R2_BLOCK_BYTES;
+          if (relubwd) mbar_wait(ybar(ew + 8 * yslot), (q.ny == 2 ? (ycount >> 1) : ycount) & 1);
           mbar_wait(tfull(buf, ph), (ti >> 1) & 1);
           tc_fence_after();
           if (et == 0 && u == h) { if (ti == 0) AE_TR2(6); AE_TR2(7); }
@@ -441,10 +454,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
           if (relubwd) {
             fence_proxy_async();
             __syncwarp();                                  // every lane is done with the y block
-            if (lane == 0) {
-              int tn = tile, un = u + 2;
-              if (un >= UNITS) { tn += gridDim.x; un = h; }
-              if (tn < num_tiles) issue_y(tn, un);
+            if (lane == 0) {                               // this slot takes the unit after next (two slots) or the next one
+              int tn = tile, un = u;
+              next_unit(tn, un);
+              if (q.ny == 2) next_unit(tn, un);
+              if (tn < num_tiles) issue_y(tn, un, yslot);
             }
           }
         }
@@ -534,10 +548,14 @@ static int launch_row2(TmaRow2& q, cudaStream_t st) {
   AE_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   cudaFuncAttributes fa;
   AE_CUDA(cudaFuncGetAttributes(&fa, k_rowgemm2<FAMILY, WT, KC, NSPLIT, NSUB>));
-  const size_t stage = (size_t)(q.epi.mode == AE_EPI_RELUBWD_STATS ? 16 : 8) * R2_BLOCK_BYTES;
-  const size_t budget = (size_t)smem_max - fa.sharedSizeBytes - 1024 - stage;   // both rings
+  const bool relubwd = q.epi.mode == AE_EPI_RELUBWD_STATS;
   const int tiles_n = q.N / PW;
   const int wn = (FAMILY == FAM_DGRAD ? 5 : 9) * q.cpt;      // weight groups per output tile
+  const size_t room = (size_t)smem_max - fa.sharedSizeBytes - 1024 - 8 * R2_BLOCK_BYTES;
+  // two y blocks per epilogue warp (the next unit's load in flight) when the rings keep at least 3 + 2 slots beside them
+  q.ny = relubwd ? ((wn < 3 ? wn : 3) * W_SLOT + 2 * A_SLOT + 16 * R2_BLOCK_BYTES <= room ? 2 : 1) : 0;
+  const size_t stage = (size_t)(8 + 8 * q.ny) * R2_BLOCK_BYTES;
+  const size_t budget = room - (size_t)8 * q.ny * R2_BLOCK_BYTES;   // both rings
   // resident weights: one n-tile whose groups fit beside at least two activation slots
   q.resident = tiles_n == 1 && wn <= R2_MAXRING && wn * W_SLOT + 2 * A_SLOT <= budget;
   q.nw = q.resident ? wn : (wn < 4 ? wn : 4);

@@ -19,7 +19,7 @@ from ae_b200 import _lib
 from tests import gpu_util as gu
 
 
-def timed(fn, nrot, iters=20):
+def timed(fn, nrot, iters=int(os.environ.get("THIN_ITERS", "20"))):
     """fn(i) launches on the current stream with buffer set i % nrot; returns microseconds per launch (graph replay)."""
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
