@@ -657,6 +657,10 @@ def run_ours(args):
             guarded("torch_gpu_baseline", lambda: torch_gpu_baseline(dev, B, xs_d, ys_d))
             guarded("dropin_loop", lambda: dropin_loop(dev, B, xs_d, ys_d, args.precision, args.backend))
             guarded("mlp_train", lambda: mlp_train_rate(dev))
+            if args.precision == "fp32" and args.backend == "tc":
+                # the same inference metric in the library's bf16 mode (one operand plane, fp32 accumulate; BASELINE's
+                # stated tolerance for it is rel <= 1e-2): reported beside the fp32-mode headline, never in its place
+                guarded("inference_bf16_mode", lambda: inference_rate(dev, "bf16", args.backend, sweep=()))
             guarded("full_pipeline_bf16", lambda: full_pipeline(dev))
         barrier()
         guarded("dp_global_4096", lambda: dp_global_batch(dev, world, rank, comm, args, 4096))

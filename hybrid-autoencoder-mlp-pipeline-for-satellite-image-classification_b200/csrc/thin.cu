@@ -25,8 +25,10 @@ namespace ae {
 //   WGRAD : partial[cta][c32][k] = sum_p wide(p,c32) * patch(p,k); partial[cta][864+c3] = sum of the thin operand
 // Both read the same staged thin rows, so the fused convT4 backward touches x / x_hat once.
 // ---------------------------------------------------------------------------------------------
+// CTAs per SM: the gather alone fits 4 (registers); the stagings of the weight gradient limit the fused backward to 3 and
+// the weight gradient with a BatchNorm-backward operand to 2 -- the register budget follows (128 / 168 / 255)
 template <bool GATHER, bool WGRAD>
-__global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wide, const float* __restrict__ w, Epilogue e,
+__global__ void __launch_bounds__(TT_THREADS, WGRAD ? (GATHER ? 3 : 2) : 4) k_thin(Operand thin, Operand wide, const float* __restrict__ w, Epilogue e,
                                                      float* __restrict__ out, float* __restrict__ partial, int batch,
                                                      const __grid_constant__ CUtensorMap xmap,
                                                      const __grid_constant__ CUtensorMap xmap2) {
@@ -78,6 +80,17 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
   const int c4 = lane & 7, kg = lane >> 3;
   int koff[7];
   float wacc[4][7];
+  // weight gradient alone (two CTAs per SM, 255 registers): a lane owns 4 channels x ALL 27 taps for every 4th pixel of its
+  // warp's row -- per pixel one 16-byte operand load and 18 patch loads feed 108 FMAs (the 4 x 7 tile above: 8 loads per 28),
+  // which takes the kernel off the shared-memory pipe (ncu: 83 % of its peak with the narrow tile)
+  constexpr bool WIDE_W = WGRAD && !GATHER;
+  float wfull[WIDE_W ? 4 : 1][WIDE_W ? 27 : 1];
+  if (WIDE_W) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 27; ++k) wfull[i][WIDE_W ? k : 0] = 0.f;
+  }
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
     int k = kg * 7 + j;
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
     }
     float4 y4[8];                                         // RELUBWD: raw outputs of this thread's pixels / channels (prefetched)
     const size_t row = (m0 + (size_t)g_r * WW + g_x0) * WC + g_c0;
-    if (GATHER && !WGRAD && e.mode == AE_EPI_RELUBWD_STATS) {   // (the fused kernel has no registers to spare: it loads in the epilogue)
+    if (GATHER && e.mode == AE_EPI_RELUBWD_STATS) {             // in flight while the tile is computed
 #pragma unroll
       for (int px = 0; px < 8; ++px) y4[px] = __ldg(reinterpret_cast<const float4*>(e.y + row + px * WC));
     }
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
         const float mu[4] = {kmu.x, kmu.y, kmu.z, kmu.w}, rs[4] = {krs.x, krs.y, krs.z, krs.w};
 #pragma unroll
         for (int px = 0; px < 8; ++px) {
-          const float4 yq = WGRAD ? __ldg(reinterpret_cast<const float4*>(e.y + row + px * WC)) : y4[px];
+          const float4 yq = y4[px];
           const float yv[4] = {yq.x, yq.y, yq.z, yq.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -247,7 +260,28 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
       }
     }
 
-    if (WGRAD) {
+    if (WIDE_W) {
+      const float* arow = as + warp * 32 * 32 + c4 * 4;
+      const float* prow = xs + 2 * warp * XS_PITCH + 3;
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int pc = kg + 4 * i;                            // kg = lane >> 3: this lane's pixel subset
+        const float4 a4 = *reinterpret_cast<const float4*>(arow + pc * 32);
+        const float* pb = prow + 2 * pc;
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const float* tp = pb + (c3 * XS_ROWS + ky) * XS_PITCH;
+            const float t0 = tp[0];
+            const float2 t12 = *reinterpret_cast<const float2*>(tp + 1);   // thin column 2*pc: even index, 8-byte aligned
+            const int k = WIDE_W ? c3 * 9 + ky * 3 : 0;
+            fma2(wfull[0][k], wfull[1][k], t0, a4.x, a4.y);             fma2(wfull[2][k], wfull[3][k], t0, a4.z, a4.w);
+            fma2(wfull[0][k + 1], wfull[1][k + 1], t12.x, a4.x, a4.y);   fma2(wfull[2][k + 1], wfull[3][k + 1], t12.x, a4.z, a4.w);
+            fma2(wfull[0][k + 2], wfull[1][k + 2], t12.y, a4.x, a4.y);   fma2(wfull[2][k + 2], wfull[3][k + 2], t12.y, a4.z, a4.w);
+          }
+      }
+    } else if (WGRAD) {
       // warp q accumulates over wide pixels q*32 .. q*32+31 of the tile (= wide row q)
       const float* arow = as + warp * 32 * 32 + c4 * 4;
       const float* prow = xs + 2 * warp * XS_PITCH;
@@ -285,10 +319,22 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin(Operand thin, Operand wi
   }
   if (WGRAD) {
     float* red = stage0 + L.wide;                       // [4 warps][32 ch][28] (stage 0's wide tile: nothing in flight any more)
+    if (WIDE_W) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 7; ++j) red[(warp * 32 + c4 * 4 + i) * 28 + kg * 7 + j] = wacc[i][j];
+        for (int k = 0; k < 27; ++k) {                      // sum over the four pixel subsets (lane bits 3, 4)
+          float v = wfull[i][WIDE_W ? k : 0];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (kg == 0) red[(warp * 32 + c4 * 4 + i) * 28 + k] = v;
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) red[(warp * 32 + c4 * 4 + i) * 28 + kg * 7 + j] = wacc[i][j];
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float sm = warp_sum(bsum[c]);
