@@ -79,6 +79,9 @@ _SIGS = {
     "ae_mlp_train_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_uint64, c_void_p, c_float, c_int, c_int,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, P(AdamConfig), c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "ae_mlp_train_step_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          C.c_uint64, c_void_p, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_size_t, P(AdamConfig), c_void_p, c_void_p, c_void_p, c_void_p]),
     "ae_mlp_forward_eval": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ae_mlp_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ae_adam_step_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,

@@ -39,6 +39,11 @@ struct MlpArgs {
   // graph-replayable step (ae_mlp_train_step): the dropout seed of launch i is seed + seed_dev[0], and the launch advances
   // seed_dev[0] and both BatchNorm layers' num_batches_tracked itself
   unsigned long long* seed_dev;
+  // epoch mode (ae_mlp_train_step_indexed): row r of the batch is row order[cursor[0] + r] of x / labels; the launch records
+  // (loss, correct) in hist[cursor[1]] and advances cursor by (B rows, 1 step) -- a whole epoch is then graph replays only
+  const long long* order;
+  long long* cursor;
+  float* hist;
   int64_t* nbt;             // [2] or NULL
   float p;
   int64_t off[10];
@@ -103,6 +108,29 @@ __device__ __forceinline__ void tile_linear(const float* __restrict__ inT, int K
   }
 }
 
+// Stage a torch Linear weight W [J][K] (row-major, K a multiple of 4) transposed into shared memory Ws [K][LD]: all of a
+// thread's 16-byte global loads are issued before the first shared-memory store (a plain element loop exposes one global
+// latency per iteration: 64 iterations for the two hidden layers, most of the eval kernel's time).
+__device__ __forceinline__ void stage_weight_T(const float* __restrict__ W, float* __restrict__ Ws, int J, int K, int LD, int tid) {
+  const int total4 = J * K / 4;
+  for (int base = 0; base < total4; base += 8 * NT) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i4 = base + u * NT + tid;
+      v[u] = i4 < total4 ? __ldg(reinterpret_cast<const float4*>(W) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i4 = base + u * NT + tid;
+      if (i4 < total4) {
+        const int i = i4 * 4, j = i / K, k = i - j * K;
+        Ws[k * LD + j] = v[u].x; Ws[(k + 1) * LD + j] = v[u].y; Ws[(k + 2) * LD + j] = v[u].z; Ws[(k + 3) * LD + j] = v[u].w;
+      }
+    }
+  }
+}
+
 // NCTA = CTAs of the one cluster that owns the batch (launch attribute): 8 for large batches; small training batches
 // (the reference trains the MLP at batch 64, NB:3443) are bound by the cluster-wide exchanges, not by arithmetic.
 template <int NCTA>
@@ -133,8 +161,8 @@ __global__ void __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
   const float* W3 = a.params + a.off[8]; const float* b3 = a.params + a.off[9];
 
   // resident weights, k-major with an odd leading dimension (conflict-free for both access directions)
-  for (int i = tid; i < H1 * D; i += NT) { const int j = i / D, k = i - j * D; W1s[k * LD1 + j] = W1[i]; }
-  for (int i = tid; i < H2 * H1; i += NT) { const int j = i / H1, k = i - j * H1; W2s[k * LD2 + j] = W2[i]; }
+  stage_weight_T(W1, W1s, H1, D, LD1, tid);
+  stage_weight_T(W2, W2s, H2, H1, LD2, tid);
   for (int i = tid; i < H2 * LD3; i += NT) W3s[i] = 0.f;
   __syncthreads();
   for (int i = tid; i < C * H2; i += NT) { const int c = i / H2, k = i - c * H2; W3s[k * LD3 + c] = W3[i]; }
@@ -143,6 +171,8 @@ __global__ void __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
   const int r0 = min(B, (int)rank * rows_per), r1 = min(B, r0 + rows_per);
   const float keep_scale = 1.f / (1.f - a.p);
   const unsigned long long seed = a.seed + (a.seed_dev ? a.seed_dev[0] : 0ull);
+  const long long row_base = a.order ? a.cursor[0] : 0;
+  auto src_row = [&](int r) -> size_t { return a.order ? (size_t)a.order[row_base + r] : (size_t)r; };
   float* c1 = coef;            // layer 1: scale, shift, mean, rstd, A, B, C  (rows of 128)
   float* c2 = coef + 7 * H1;   // layer 2
   __syncthreads();
@@ -156,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
         const int nv = min(CHUNK, r1 - c0);
         for (int i = tid; i < D * CHUNK; i += NT) {
           const int r = i / D, k = i - r * D;
-          stg0[k * CHUNK + r] = r < nv ? a.x[(size_t)(c0 + r) * D + k] : 0.f;
+          stg0[k * CHUNK + r] = r < nv ? a.x[src_row(c0 + r) * D + k] : 0.f;
         }
         __syncthreads();
         tile_linear<H1>(stg0, D, W1s, LD1, b1, a.h1, c0, nv, &s1, &s2);
@@ -269,7 +299,7 @@ __global__ void __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
         for (int c = 1; c < C; ++c) if (row[c] > mx) { mx = row[c]; am = c; }
         float se = 0.f;
         for (int c = 0; c < C; ++c) se += expf(row[c] - mx);
-        const int lab = (int)a.labels[c0 + tid];
+        const int lab = (int)a.labels[src_row(c0 + tid)];
         lsum += logf(se) + mx - row[lab];
         ok += (am == lab);
         if (a.flags & MLP_BWD) {
@@ -486,7 +516,7 @@ __global__ void __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
         }
         for (int i = tid; i < D * CHUNK; i += NT) {
           const int r = i / D, k = i - r * D;
-          stg1[k * CHUNK + r] = r < nv ? a.x[(size_t)(c0 + r) * D + k] : 0.f;
+          stg1[k * CHUNK + r] = r < nv ? a.x[src_row(c0 + r) * D + k] : 0.f;
         }
         __syncthreads();
         for (int q = 0; q < CHUNK / 4; ++q) {
@@ -513,11 +543,15 @@ __global__ void __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
     }
   }
   (void)misc;
-  if (a.seed_dev || a.nbt) {
-    cl.sync();                                 // every CTA has read the seed
+  if (a.seed_dev || a.nbt || a.cursor) {
+    cl.sync();                                 // every CTA has read the seed and the cursor
     if (rank == 0 && tid == 0) {
       if (a.seed_dev) a.seed_dev[0] += 0x9E3779B97F4A7C15ull;
       if (a.nbt && training) { a.nbt[0] += 1; a.nbt[1] += 1; }
+      if (a.cursor) {
+        if (a.hist) { a.hist[2 * a.cursor[1]] = a.loss[0]; a.hist[2 * a.cursor[1] + 1] = (float)a.correct[0]; }   // written by this thread above
+        a.cursor[0] += B; a.cursor[1] += 1;
+      }
     }
   }
 }
@@ -570,8 +604,8 @@ __global__ void __launch_bounds__(NT, 1) k_mlp_eval(const float* __restrict__ pa
   const float* W2 = params + lay.off[4]; const float* b2 = params + lay.off[5];
   const float* g2 = params + lay.off[6]; const float* be2 = params + lay.off[7];
   const float* W3 = params + lay.off[8]; const float* b3 = params + lay.off[9];
-  for (int i = tid; i < H1 * D; i += NT) { const int j = i / D, k = i - j * D; W1s[k * LD1 + j] = W1[i]; }
-  for (int i = tid; i < H2 * H1; i += NT) { const int j = i / H1, k = i - j * H1; W2s[k * LD2 + j] = W2[i]; }
+  stage_weight_T(W1, W1s, H1, D, LD1, tid);
+  stage_weight_T(W2, W2s, H2, H1, LD2, tid);
   for (int i = tid; i < H2 * LD3; i += NT) W3s[i] = 0.f;
   for (int j = tid; j < H1; j += NT) {
     const float rstd = 1.f / sqrtf(running[H1 + j] + BN_EPS_F), s = g1[j] * rstd;
@@ -759,6 +793,35 @@ int ae_mlp_train_step(float* params, float* grads, float* bn_running, int64_t* b
   a.dlogits_in = nullptr; a.logits = logits; a.loss = loss; a.correct = correct;
   a.h1 = w.h1; a.h2 = w.h2; a.d1 = w.d1; a.d2 = w.d2; a.dlog = w.dlog; a.keep = w.keep; a.bnc = w.bnc;
   a.B = batch; a.D = input_dim; a.C = num_classes; a.seed = dropout_seed; a.seed_dev = (unsigned long long*)seed_dev; a.nbt = bn_steps;
+  a.p = dropout_p;
+  a.flags = MLP_FWD | MLP_TRAIN | MLP_CE | MLP_BWD;
+  AE_TRY(mlp_launch(a, (cudaStream_t)stream));
+  int64_t off[10];
+  const int64_t n = mlp_layout(input_dim, num_classes, off, nullptr);
+  return adam_step_flat(params, grads, adam_m, adam_v, n, adam->lr, adam->beta1, adam->beta2, adam->eps, adam->weight_decay, 1.f,
+                        step_dev, (cudaStream_t)stream);
+}
+
+// The same step reading its batch through an index: rows order[cursor[0] ..] of x_all / labels_all (cursor = int64[2]: rows
+// consumed, steps done); (loss, correct) of step i land in hist[i].  One graph replay per batch runs an epoch.
+int ae_mlp_train_step_indexed(float* params, float* grads, float* bn_running, int64_t* bn_steps, const float* x_all,
+                              const int64_t* labels_all, const int64_t* order, int64_t* cursor, float* hist, uint64_t dropout_seed,
+                              uint64_t* seed_dev, float dropout_p, int batch, int input_dim, int num_classes, float* logits,
+                              float* loss, int* correct, void* workspace, size_t workspace_bytes, const ae_adam_config_t* adam,
+                              float* adam_m, float* adam_v, int* step_dev, ae_stream_t stream) {
+  AE_CHECK(params && grads && bn_running && x_all && labels_all && order && cursor && seed_dev && workspace && adam && adam_m &&
+               adam_v && step_dev && loss && correct,
+           "ae_mlp_train_step_indexed: null argument");
+  AE_CHECK(workspace_bytes >= mlp_carve(batch, nullptr, nullptr), "ae_mlp_train_step_indexed: workspace too small");
+  AE_CHECK(dropout_p >= 0.f && dropout_p < 1.f, "ae_mlp_train_step_indexed: dropout_p out of range");
+  MlpWs w;
+  mlp_carve(batch, (char*)workspace, &w);
+  MlpArgs a{};
+  a.params = params; a.grads = grads; a.running = bn_running; a.x = x_all; a.labels = labels_all; a.keep_in = nullptr;
+  a.dlogits_in = nullptr; a.logits = logits; a.loss = loss; a.correct = correct;
+  a.h1 = w.h1; a.h2 = w.h2; a.d1 = w.d1; a.d2 = w.d2; a.dlog = w.dlog; a.keep = w.keep; a.bnc = w.bnc;
+  a.B = batch; a.D = input_dim; a.C = num_classes; a.seed = dropout_seed; a.seed_dev = (unsigned long long*)seed_dev; a.nbt = bn_steps;
+  a.order = (const long long*)order; a.cursor = (long long*)cursor; a.hist = hist;
   a.p = dropout_p;
   a.flags = MLP_FWD | MLP_TRAIN | MLP_CE | MLP_BWD;
   AE_TRY(mlp_launch(a, (cudaStream_t)stream));

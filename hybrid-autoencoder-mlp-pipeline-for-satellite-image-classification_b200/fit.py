@@ -99,29 +99,42 @@ def train_epoch_mlp(clf, optimizer, X: torch.Tensor, y: torch.Tensor, batch_size
     n, dev = int(X.shape[0]), X.device
     order = torch.randperm(n, device=dev, generator=generator) if shuffle else torch.arange(n, device=dev)
     steps = (n + batch_size - 1) // batch_size
-    hist = torch.zeros(steps, 2, dtype=torch.float32, device=dev)
-    sizes = []
-    cache = clf.__dict__.setdefault("_train_steps", {})       # one captured step per (optimizer, batch size)
-    explicit_mask = clf._dropout_keep_override is not None     # test hook: the explicit-mask path is not graph-captured
-    for k in range(steps):
-        idx = order[k * batch_size:(k + 1) * batch_size]
-        b = int(idx.numel())
-        if explicit_mask:
+    cache = clf.__dict__.setdefault("_train_steps", {})       # captured steps per (optimizer, batch size[, data])
+    if clf._dropout_keep_override is not None:                 # test hook: the explicit-mask path is not graph-captured
+        hist = torch.zeros(steps, 2, dtype=torch.float32, device=dev)
+        sizes = []
+        for k in range(steps):
+            idx = order[k * batch_size:(k + 1) * batch_size]
             xb, yb = X.index_select(0, idx), y.index_select(0, idx)
             optimizer.zero_grad()
             loss, correct, _ = clf.fused_step_grads(xb, yb)
             optimizer.step()
-        else:
-            step = cache.get((id(optimizer), b))
-            if step is None or not step.valid():
-                step = cache[(id(optimizer), b)] = MLPTrainStep(clf, optimizer, b, dev)
-            torch.index_select(X, 0, idx, out=step.x)
-            torch.index_select(y, 0, idx, out=step.y)
+            hist[k, 0:1].copy_(loss, non_blocking=True)
+            hist[k, 1:2].copy_(correct, non_blocking=True)    # int32 -> float32 (exact below 2^24)
+            sizes.append(int(idx.numel()))
+    else:
+        # Epoch mode: the captured step gathers its own batch through `order` and records (loss, correct) itself; the host
+        # issues one graph replay per batch.  The buffers the graphs address live in the per-data cache entry.
+        if not (X.dtype == torch.float32 and y.dtype == torch.int64 and X.is_contiguous() and y.is_contiguous()):
+            raise TypeError("train_epoch_mlp: X must be contiguous float32 [N,D] and y contiguous int64 [N]")
+        key = (id(optimizer), X.data_ptr(), y.data_ptr(), n, batch_size)
+        ent = cache.get(key)
+        if ent is None or ent["X"] is not X or ent["y"] is not y or not all(s_.valid() for s_ in ent["steps"].values()):
+            for old_key in [k_ for k_ in cache if k_[0] == id(optimizer)]:
+                del cache[old_key]                             # one data set per optimizer at a time: drop stale graphs
+            ent = cache[key] = {"X": X, "y": y, "order": torch.zeros(n, dtype=torch.int64, device=dev),
+                                "cursor": torch.zeros(2, dtype=torch.int64, device=dev),
+                                "hist": torch.zeros(steps, 2, dtype=torch.float32, device=dev), "steps": {}}
+        ent["order"].copy_(order)
+        ent["cursor"].zero_()
+        sizes = [min(batch_size, n - k * batch_size) for k in range(steps)]
+        for b in sizes:
+            step = ent["steps"].get(b)
+            if step is None:
+                step = ent["steps"][b] = MLPTrainStep(clf, optimizer, b, dev,
+                                                      epoch=(X, y, ent["order"], ent["cursor"], ent["hist"]))
             step.run()
-            loss, correct = step.loss, step.correct
-        hist[k, 0:1].copy_(loss, non_blocking=True)
-        hist[k, 1:2].copy_(correct, non_blocking=True)        # int32 -> float32 (exact below 2^24)
-        sizes.append(b)
+        hist = ent["hist"]
     h = hist.cpu()
     tot = sum(sizes)
     return sum(v * b for v, b in zip(h[:, 0].tolist(), sizes)) / tot, float(h[:, 1].sum()) / tot

@@ -194,9 +194,13 @@ class MLPTrainStep:
     backward) and the fused flat Adam -- on fixed device buffers.  Nothing that changes between steps is baked in: the
     dropout seed advances on the device.  `load` copies / gathers a batch into the buffers, `run` replays."""
 
-    def __init__(self, clf, optimizer: Adam, batch: int, device=None):
+    def __init__(self, clf, optimizer: Adam, batch: int, device=None, epoch=None):
+        """`epoch` = (X, y, order, cursor, hist): epoch mode -- the captured step reads its batch as rows
+        order[cursor[0] ..] of the device-resident X / y, stores (loss, correct) in hist[cursor[1]] and advances the cursor
+        itself (ae_mlp_train_step_indexed), so an epoch is one `run()` per batch and nothing else on the host."""
         lib = _lib.load()
         self.clf, self.opt, self.batch = clf, optimizer, int(batch)
+        self.epoch = epoch
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.device = dev
         st = clf._state
@@ -220,10 +224,20 @@ class MLPTrainStep:
         stream.wait_stream(torch.cuda.current_stream(dev))
 
         def call():
+            cur = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if epoch is not None:
+                X, y, order, cursor, hist = epoch
+                assert X.dtype == torch.float32 and y.dtype == torch.int64 and X.is_contiguous() and y.is_contiguous()
+                assert order.dtype == torch.int64 and cursor.dtype == torch.int64 and cursor.numel() == 2 and hist.dtype == torch.float32
+                check(lib.ae_mlp_train_step_indexed(ptr(st.flat.data), ptr(st.flat.grad), ptr(st.running), ptr(st.steps), ptr(X), ptr(y),
+                                                    ptr(order), ptr(cursor), ptr(hist), seed, ptr(self.seed_dev), float(clf.net[3].p),
+                                                    batch, d, c, ptr(self.logits), ptr(self.loss), ptr(self.correct), st.ws_ptr,
+                                                    st.ws_bytes, C.byref(cfg), ptr(ast["m"]), ptr(ast["v"]), ptr(ast["step"]), cur))
+                return
             check(lib.ae_mlp_train_step(ptr(st.flat.data), ptr(st.flat.grad), ptr(st.running), ptr(st.steps), ptr(self.x), ptr(self.y),
                                         seed, ptr(self.seed_dev), float(clf.net[3].p), batch, d, c, ptr(self.logits), ptr(self.loss),
                                         ptr(self.correct), st.ws_ptr, st.ws_bytes, C.byref(cfg), ptr(ast["m"]), ptr(ast["v"]),
-                                        ptr(ast["step"]), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                                        ptr(ast["step"]), cur))
         # Collect garbage BEFORE the capture and capture in relaxed mode: a cyclic-GC pass that happens to run inside the capture
         # window may finalise an old TrainStep, whose close() synchronises its own stream -- in the default (global) mode that
         # unrelated call invalidates this capture.

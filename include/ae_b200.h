@@ -232,6 +232,14 @@ int ae_mlp_train_step(float* params, float* grads, float* bn_running, int64_t* b
                       uint64_t dropout_seed, uint64_t* seed_dev, float dropout_p, int batch, int input_dim, int num_classes,
                       float* logits, float* loss, int* correct, void* workspace, size_t workspace_bytes,
                       const ae_adam_config_t* adam, float* adam_m, float* adam_v, int* step_dev, ae_stream_t stream);
+/* The same step with its batch read through an index (NB:3443 DataLoader(shuffle=True) + NB:3476-3482): row r of the batch is
+ * row order[cursor[0] + r] of x_all / labels_all; cursor = int64[2] {rows consumed, steps done} advances on the device and
+ * (loss, correct) of step i are stored in hist[i][0..1].  An epoch is then one graph replay per batch, nothing else. */
+int ae_mlp_train_step_indexed(float* params, float* grads, float* bn_running, int64_t* bn_steps, const float* x_all,
+                              const int64_t* labels_all, const int64_t* order, int64_t* cursor, float* hist, uint64_t dropout_seed,
+                              uint64_t* seed_dev, float dropout_p, int batch, int input_dim, int num_classes, float* logits,
+                              float* loss, int* correct, void* workspace, size_t workspace_bytes, const ae_adam_config_t* adam,
+                              float* adam_m, float* adam_v, int* step_dev, ae_stream_t stream);
 int ae_mlp_forward_eval(const float* params, const float* bn_running, const float* x, int batch, int input_dim,
                         int num_classes, float* logits, int64_t* argmax /*or NULL*/, ae_stream_t stream);
 /* Backward of a preceding training-mode ae_mlp_fwd_bwd_ce call made with labels == NULL (forward only,

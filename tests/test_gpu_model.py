@@ -635,3 +635,50 @@ def test_mlp_train_step_graph_matches_oracle_loop(batch, cluster, monkeypatch):
     # the first Adam step moves every weight by ~lr: all of them within 2 lr of the oracle, nearly all of them the same way
     d = (after_first["net.4.weight"].cpu() - ref_after_first["net.4.weight"]).abs()
     assert float(d.max()) <= 2.01 * lr and float((d > 0.1 * lr).float().mean()) <= 1e-2
+
+
+def test_mlp_epoch_mode_matches_stepping_by_hand():
+    """fit.train_epoch_mlp replays one captured step per batch that gathers its own rows through the epoch's permutation and
+    records (loss, correct) on the device (ae_mlp_train_step_indexed).  With dropout off it must reproduce, bit for bit, an
+    MLPTrainStep fed by hand with the same batches -- ragged tail batch included -- and a second epoch must re-use the graphs."""
+    from ae_b200 import fit
+    seed, lr, wd, n, bs = 23, 1e-3, 1e-4, 150, 64
+    st = seeded.seeded_state(seeded.mlp_state_shapes(64, 10), seed)
+    rs = np.random.RandomState(7)
+    X = torch.from_numpy(rs.standard_normal((n, 64)).astype(np.float32)).to(gu.dev())
+    y = seeded.seeded_labels(n, seed).to(gu.dev())
+
+    def make():
+        clf = ae_b200.MLP(64, 10)
+        clf.load_state_dict(st)
+        clf = clf.to(gu.dev()).train()
+        clf.net[3].p = 0.0
+        clf._state.prepare(gu.dev(), bs)
+        return clf, ae_b200.Adam(clf.parameters(), lr=lr, weight_decay=wd)
+
+    gen = torch.Generator(device=gu.dev()).manual_seed(5)
+    orders = [torch.randperm(n, device=gu.dev(), generator=gen) for _ in range(2)]
+    # by hand
+    clf_a, opt_a = make()
+    steps = {b: ae_b200.MLPTrainStep(clf_a, opt_a, b) for b in (64, 22)}
+    hand = []
+    for order in orders:
+        tot_l, tot_c = 0.0, 0
+        for k in range(0, n, bs):
+            idx = order[k:k + bs]
+            s = steps[int(idx.numel())]
+            s.x.copy_(X[idx]); s.y.copy_(y[idx])
+            s.run()
+            tot_l += float(s.loss) * int(idx.numel()); tot_c += int(s.correct)
+        hand.append((tot_l / n, tot_c / n))
+    # epoch mode with the same permutations
+    clf_b, opt_b = make()
+    gen = torch.Generator(device=gu.dev()).manual_seed(5)
+    got = [fit.train_epoch_mlp(clf_b, opt_b, X, y, bs, True, gen) for _ in range(2)]
+    torch.cuda.synchronize()
+    assert len(clf_b._train_steps) == 1 and sorted(next(iter(clf_b._train_steps.values()))["steps"]) == [22, 64]
+    for (la, ca), (lb, cb) in zip(hand, got):
+        assert abs(la - lb) <= 1e-6 * max(1.0, abs(la)) and ca == cb
+    sa, sb = clf_a.state_dict(), clf_b.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
