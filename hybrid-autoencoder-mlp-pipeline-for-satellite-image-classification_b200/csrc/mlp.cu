@@ -111,18 +111,19 @@ __device__ __forceinline__ void tile_linear(const float* __restrict__ inT, int K
 // Stage a torch Linear weight W [J][K] (row-major, K a multiple of 4) transposed into shared memory Ws [K][LD]: all of a
 // thread's 16-byte global loads are issued before the first shared-memory store (a plain element loop exposes one global
 // latency per iteration: 64 iterations for the two hidden layers, most of the eval kernel's time).
+template <int NTHREADS = NT>
 __device__ __forceinline__ void stage_weight_T(const float* __restrict__ W, float* __restrict__ Ws, int J, int K, int LD, int tid) {
   const int total4 = J * K / 4;
-  for (int base = 0; base < total4; base += 8 * NT) {
+  for (int base = 0; base < total4; base += 8 * NTHREADS) {
     float4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int i4 = base + u * NT + tid;
+      const int i4 = base + u * NTHREADS + tid;
       v[u] = i4 < total4 ? __ldg(reinterpret_cast<const float4*>(W) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int i4 = base + u * NT + tid;
+      const int i4 = base + u * NTHREADS + tid;
       if (i4 < total4) {
         const int i = i4 * 4, j = i / K, k = i - j * K;
         Ws[k * LD + j] = v[u].x; Ws[(k + 1) * LD + j] = v[u].y; Ws[(k + 2) * LD + j] = v[u].z; Ws[(k + 3) * LD + j] = v[u].w;
@@ -558,6 +559,438 @@ __global__ void __launch_bounds__(NT, 1) k_mlp(MlpArgs a) {
 
 
 // ---------------------------------------------------------------------------------------------
+// k_mlp_small: the whole training step's forward + cross-entropy + backward for a batch of at most 64 rows (the reference
+// trains the MLP at batch 64, NB:3443) in ONE CTA of 512 threads with every intermediate resident in shared memory.
+// The cluster kernel above spreads the rows over up to 8 CTAs and pays ~10 cluster-wide exchanges plus a global round trip
+// of every intermediate per phase; at this size that latency, not arithmetic, was the step (82 us).  Here the only
+// synchronisation is __syncthreads, activations are kept k-major ([feature][row]) so that GEMM operands are 16-byte loads,
+// and each thread's outputs stay in registers across the BatchNorm statistics.  Same arithmetic as k_mlp (same dropout
+// hash, fp32 partial sums combined in double, BatchNorm backward as A*dz + B*(h-mean) + C).
+// ---------------------------------------------------------------------------------------------
+static constexpr int SB = 64, NTS = 512, LW1 = 130, LW2 = 66;
+static constexpr int SP = 68;   // row pitch of the [feature][row] buffers: 16-byte loads of 32 consecutive features hit distinct banks
+static constexpr size_t MLP_SMALL_SMEM =
+    sizeof(float) * (64 * LW1 + H1 * LW2 + H2 * LD3 + 64 * SP + 2 * H1 * SP + 2 * H2 * SP + SB * LD3 + 16 * SP + 2048 + 14 * H1 + 64);
+
+__device__ __forceinline__ void fma2s(float& d0, float& d1, float a, float b0, float b1) {
+  const float2 r = __ffma2_rn(make_float2(a, a), make_float2(b0, b1), make_float2(d0, d1));
+  d0 = r.x; d1 = r.y;
+}
+
+__global__ void __launch_bounds__(NTS, 1) k_mlp_small(MlpArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, D = a.D, C = a.C, B = a.B;
+  float* W1s = sm;                       // [D][LW1]   W1s[k][j] = W1[j][k]
+  float* W2s = W1s + 64 * LW1;           // [128][LW2] W2s[k][j] = W2[j][k]
+  float* W3s = W2s + H1 * LW2;           // [64][LD3]  W3s[k][c] = W3[c][k]
+  float* xT = W3s + H2 * LD3;            // [D][SB]
+  float* h1T = xT + 64 * SP;             // [128][SB] raw layer-1 outputs
+  float* a1T = h1T + H1 * SP;            // [128][SB] dropout(relu(bn1(h1)));  later dh1
+  float* h2T = a1T + H1 * SP;            // [64][SB]
+  float* a2T = h2T + H2 * SP;            // [64][SB] relu(bn2(h2));  later dh2
+  float* dls = a2T + H2 * SP;            // [SB][LD3] logits, then dlogits
+  float* dlT = dls + SB * LD3;           // [16][SB]  dlogits, class-major
+  float* part = dlT + 16 * SP;           // [row groups][2][columns] partial statistics (2048 floats)
+  float* c1 = part + 2048;               // [7][128]: scale, shift, mean, rstd, A, B, C
+  float* c2 = c1 + 7 * H1;
+  float* misc = c2 + 7 * H1;             // [64]
+
+  const float* W1 = a.params + a.off[0]; const float* b1 = a.params + a.off[1];
+  const float* g1 = a.params + a.off[2]; const float* be1 = a.params + a.off[3];
+  const float* W2 = a.params + a.off[4]; const float* b2 = a.params + a.off[5];
+  const float* g2 = a.params + a.off[6]; const float* be2 = a.params + a.off[7];
+  const float* W3 = a.params + a.off[8]; const float* b3 = a.params + a.off[9];
+  float* gp = a.grads;
+  const unsigned long long seed = a.seed + (a.seed_dev ? a.seed_dev[0] : 0ull);
+  const long long row_base = a.order ? a.cursor[0] : 0;
+  const float keep_scale = 1.f / (1.f - a.p);
+  const bool drop = a.p > 0.f;
+#ifdef AE_TRACE
+  long long tr_t[12]; int tr_n = 0;
+#define MLP_TR() do { if (tid == 0) tr_t[tr_n++] = clock64(); } while (0)
+#else
+#define MLP_TR() do {} while (0)
+#endif
+  MLP_TR();
+
+  // ---- stage: weights (transposed), the batch (gathered, transposed, zero rows behind B) ----
+  stage_weight_T<NTS>(W1, W1s, H1, D, LW1, tid);
+  stage_weight_T<NTS>(W2, W2s, H2, H1, LW2, tid);
+  for (int i = tid; i < H2 * LD3; i += NTS) {
+    const int k = i / LD3, c = i - k * LD3;
+    W3s[i] = c < C ? W3[c * H2 + k] : 0.f;
+  }
+  {
+    const int d4 = D / 4;
+    for (int i = tid; i < SB * d4; i += NTS) {
+      const int r = i / d4, k = (i - r * d4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < B) {
+        const size_t row = a.order ? (size_t)a.order[row_base + r] : (size_t)r;
+        v = __ldg(reinterpret_cast<const float4*>(a.x + row * D + k));
+      }
+      xT[(k + 0) * SP + r] = v.x; xT[(k + 1) * SP + r] = v.y; xT[(k + 2) * SP + r] = v.z; xT[(k + 3) * SP + r] = v.w;
+    }
+  }
+  __syncthreads();
+
+  MLP_TR();
+  // =============================== forward ===============================
+  // ---- layer 1: thread = 8 rows x 2 columns of h1 [64 x 128] ----
+  {
+    const int j0 = (tid & 63) * 2, rg = tid >> 6, r0 = rg * 8;
+    float acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) {
+      const float4 x0 = *reinterpret_cast<const float4*>(xT + k * SP + r0), x1 = *reinterpret_cast<const float4*>(xT + k * SP + r0 + 4);
+      const float2 w = *reinterpret_cast<const float2*>(W1s + k * LW1 + j0);
+      fma2s(acc[0][0], acc[0][1], x0.x, w.x, w.y); fma2s(acc[1][0], acc[1][1], x0.y, w.x, w.y);
+      fma2s(acc[2][0], acc[2][1], x0.z, w.x, w.y); fma2s(acc[3][0], acc[3][1], x0.w, w.x, w.y);
+      fma2s(acc[4][0], acc[4][1], x1.x, w.x, w.y); fma2s(acc[5][0], acc[5][1], x1.y, w.x, w.y);
+      fma2s(acc[6][0], acc[6][1], x1.z, w.x, w.y); fma2s(acc[7][0], acc[7][1], x1.w, w.x, w.y);
+    }
+    const float bb[2] = {b1[j0], b1[j0 + 1]};
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        acc[i][c] += bb[c];
+        if (r0 + i < B) { s1[c] += acc[i][c]; s2[c] += acc[i][c] * acc[i][c]; }
+      }
+    part[(rg * 2 + 0) * H1 + j0] = s1[0]; part[(rg * 2 + 0) * H1 + j0 + 1] = s1[1];
+    part[(rg * 2 + 1) * H1 + j0] = s2[0]; part[(rg * 2 + 1) * H1 + j0 + 1] = s2[1];
+    __syncthreads();
+    if (tid < H1) {
+      double S1 = 0.0, S2 = 0.0;
+      for (int g = 0; g < 8; ++g) { S1 += (double)part[(g * 2 + 0) * H1 + tid]; S2 += (double)part[(g * 2 + 1) * H1 + tid]; }
+      const double m = S1 / B;
+      double v = S2 / B - m * m;
+      if (v < 0.0) v = 0.0;
+      if (a.running) {
+        const double unb = B > 1 ? v * B / (B - 1.0) : v;
+        a.running[tid] = (float)(0.9 * (double)a.running[tid] + 0.1 * m);
+        a.running[H1 + tid] = (float)(0.9 * (double)a.running[H1 + tid] + 0.1 * unb);
+      }
+      const float mean = (float)m, rstd = 1.f / sqrtf((float)v + BN_EPS_F), sc = g1[tid] * rstd;
+      c1[tid] = sc; c1[H1 + tid] = be1[tid] - mean * sc; c1[2 * H1 + tid] = mean; c1[3 * H1 + tid] = rstd;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = j0 + c;
+      const float sc = c1[j], sh = c1[H1 + j];
+      float hv[8], av[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        float h = acc[i][c], v = fmaxf(fmaf(h, sc, sh), 0.f);
+        if (drop) v = (hash_u32(seed, r, j) * (1.0f / 4294967296.0f)) >= a.p ? v * keep_scale : 0.f;
+        if (r >= B) { h = 0.f; v = 0.f; }
+        hv[i] = h; av[i] = v;
+      }
+      *reinterpret_cast<float4*>(h1T + j * SP + r0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      *reinterpret_cast<float4*>(h1T + j * SP + r0 + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      *reinterpret_cast<float4*>(a1T + j * SP + r0) = make_float4(av[0], av[1], av[2], av[3]);
+      *reinterpret_cast<float4*>(a1T + j * SP + r0 + 4) = make_float4(av[4], av[5], av[6], av[7]);
+    }
+    __syncthreads();
+  }
+  MLP_TR();
+  // ---- layer 2: thread = 4 rows x 2 columns of h2 [64 x 64] ----
+  {
+    const int j0 = (tid & 31) * 2, rg = tid >> 5, r0 = rg * 4;
+    float acc[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 4
+    for (int k = 0; k < H1; ++k) {
+      const float4 x0 = *reinterpret_cast<const float4*>(a1T + k * SP + r0);
+      const float2 w = *reinterpret_cast<const float2*>(W2s + k * LW2 + j0);
+      fma2s(acc[0][0], acc[0][1], x0.x, w.x, w.y); fma2s(acc[1][0], acc[1][1], x0.y, w.x, w.y);
+      fma2s(acc[2][0], acc[2][1], x0.z, w.x, w.y); fma2s(acc[3][0], acc[3][1], x0.w, w.x, w.y);
+    }
+    const float bb[2] = {b2[j0], b2[j0 + 1]};
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        acc[i][c] += bb[c];
+        if (r0 + i < B) { s1[c] += acc[i][c]; s2[c] += acc[i][c] * acc[i][c]; }
+      }
+    part[(rg * 2 + 0) * H2 + j0] = s1[0]; part[(rg * 2 + 0) * H2 + j0 + 1] = s1[1];
+    part[(rg * 2 + 1) * H2 + j0] = s2[0]; part[(rg * 2 + 1) * H2 + j0 + 1] = s2[1];
+    __syncthreads();
+    if (tid < H2) {
+      double S1 = 0.0, S2 = 0.0;
+      for (int g = 0; g < 16; ++g) { S1 += (double)part[(g * 2 + 0) * H2 + tid]; S2 += (double)part[(g * 2 + 1) * H2 + tid]; }
+      const double m = S1 / B;
+      double v = S2 / B - m * m;
+      if (v < 0.0) v = 0.0;
+      if (a.running) {
+        const double unb = B > 1 ? v * B / (B - 1.0) : v;
+        a.running[2 * H1 + tid] = (float)(0.9 * (double)a.running[2 * H1 + tid] + 0.1 * m);
+        a.running[2 * H1 + H2 + tid] = (float)(0.9 * (double)a.running[2 * H1 + H2 + tid] + 0.1 * unb);
+      }
+      const float mean = (float)m, rstd = 1.f / sqrtf((float)v + BN_EPS_F), sc = g2[tid] * rstd;
+      c2[tid] = sc; c2[H1 + tid] = be2[tid] - mean * sc; c2[2 * H1 + tid] = mean; c2[3 * H1 + tid] = rstd;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = j0 + c;
+      const float sc = c2[j], sh = c2[H1 + j];
+      float hv[4], av[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = r0 + i < B;
+        hv[i] = ok ? acc[i][c] : 0.f;
+        av[i] = ok ? fmaxf(fmaf(acc[i][c], sc, sh), 0.f) : 0.f;
+      }
+      *reinterpret_cast<float4*>(h2T + j * SP + r0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      *reinterpret_cast<float4*>(a2T + j * SP + r0) = make_float4(av[0], av[1], av[2], av[3]);
+    }
+    __syncthreads();
+  }
+  MLP_TR();
+  // ---- layer 3 + cross-entropy ----
+  for (int o = tid; o < SB * C; o += NTS) {
+    const int r = o & (SB - 1), c = o >> 6;
+    float acc = b3[c];
+#pragma unroll 8
+    for (int k = 0; k < H2; ++k) acc = fmaf(a2T[k * SP + r], W3s[k * LD3 + c], acc);
+    dls[r * LD3 + c] = acc;
+    if (r < B && a.logits) a.logits[(size_t)r * C + c] = acc;
+  }
+  __syncthreads();
+  if (tid < SB) {
+    float lterm = 0.f;
+    int ok = 0;
+    float* row = dls + tid * LD3;
+    if (tid < B) {
+      float mx = row[0]; int am = 0;
+      for (int c = 1; c < C; ++c) if (row[c] > mx) { mx = row[c]; am = c; }
+      float se = 0.f;
+      for (int c = 0; c < C; ++c) se += expf(row[c] - mx);
+      const size_t src = a.order ? (size_t)a.order[row_base + tid] : (size_t)tid;
+      const int lab = (int)a.labels[src];
+      lterm = logf(se) + mx - row[lab];
+      ok = am == lab;
+      const float inv = 1.f / ((float)B * se);
+      for (int c = 0; c < C; ++c) {
+        const float d = expf(row[c] - mx) * inv - (c == lab ? 1.f / (float)B : 0.f);
+        row[c] = d; dlT[c * SP + tid] = d;
+      }
+    } else {
+      for (int c = 0; c < C; ++c) { row[c] = 0.f; dlT[c * SP + tid] = 0.f; }
+    }
+    lterm = warp_sum(lterm);
+    for (int o = 16; o > 0; o >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, o);
+    if ((tid & 31) == 0) { misc[(tid >> 5) * 2] = lterm; misc[(tid >> 5) * 2 + 1] = (float)ok; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (a.loss) a.loss[0] = (float)(((double)misc[0] + (double)misc[2]) / B);
+    if (a.correct) a.correct[0] = (int)(misc[1] + misc[3] + 0.5f);
+  }
+
+  MLP_TR();
+  // =============================== backward ===============================
+  // ---- dW3, db3; dz2 = (dlogits W3) * relu'(bn2(h2)) kept in registers, its statistics ----
+  {
+    for (int o = tid; o < C * H2; o += NTS) {
+      const int c = o >> 6, k = o & (H2 - 1);
+      float s = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < SB / 4; ++q) {
+        const float4 dv = *reinterpret_cast<const float4*>(dlT + c * SP + q * 4), av = *reinterpret_cast<const float4*>(a2T + k * SP + q * 4);
+        s = fmaf(dv.x, av.x, fmaf(dv.y, av.y, fmaf(dv.z, av.z, fmaf(dv.w, av.w, s))));
+      }
+      gp[a.off[8] + o] = s;
+    }
+    if (tid < C) {
+      float s = 0.f;
+      for (int r = 0; r < SB; ++r) s += dlT[tid * SP + r];
+      gp[a.off[9] + tid] = s;
+    }
+    const int j0 = (tid & 31) * 2, rg = tid >> 5, r0 = rg * 4;
+    float d[4][2], xh[4][2];
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = j0 + c;
+      const float sc = c2[j], sh = c2[H1 + j], mean = c2[2 * H1 + j], rstd = c2[3 * H1 + j];
+      const float4 hv4 = *reinterpret_cast<const float4*>(h2T + j * SP + r0);
+      const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float t = 0.f;
+        for (int cc = 0; cc < C; ++cc) t = fmaf(dls[(r0 + i) * LD3 + cc], W3s[j * LD3 + cc], t);
+        t = fmaf(hv[i], sc, sh) > 0.f ? t : 0.f;          // rows behind B: dlogits are zero
+        d[i][c] = t;
+        xh[i][c] = (hv[i] - mean) * rstd;
+        s1[c] += t; s2[c] += t * xh[i][c];
+      }
+    }
+    part[(rg * 2 + 0) * H2 + j0] = s1[0]; part[(rg * 2 + 0) * H2 + j0 + 1] = s1[1];
+    part[(rg * 2 + 1) * H2 + j0] = s2[0]; part[(rg * 2 + 1) * H2 + j0 + 1] = s2[1];
+    __syncthreads();                                         // dW3 has read a2T; the partials are in
+    if (tid < H2) {
+      double S1 = 0.0, S2 = 0.0;
+      for (int g = 0; g < 16; ++g) { S1 += (double)part[(g * 2 + 0) * H2 + tid]; S2 += (double)part[(g * 2 + 1) * H2 + tid]; }
+      const double rstd = c2[3 * H1 + tid];
+      const double A = (double)g2[tid] * rstd, Bc = -A * rstd * S2 / B, Cc = -A * S1 / B;
+      c2[4 * H1 + tid] = (float)A; c2[5 * H1 + tid] = (float)Bc; c2[6 * H1 + tid] = (float)Cc;
+      gp[a.off[6] + tid] = (float)S2; gp[a.off[7] + tid] = (float)S1; gp[a.off[5] + tid] = 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = j0 + c;
+      const float A = c2[4 * H1 + j], Bc = c2[5 * H1 + j], Cc = c2[6 * H1 + j], rinv = 1.f / c2[3 * H1 + j];
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = r0 + i < B ? fmaf(A, d[i][c], fmaf(Bc, xh[i][c] * rinv, Cc)) : 0.f;   // xh/rstd = h - mean
+      *reinterpret_cast<float4*>(a2T + j * SP + r0) = make_float4(o[0], o[1], o[2], o[3]);                   // dh2^T
+    }
+    __syncthreads();
+  }
+  MLP_TR();
+  // ---- dW2 = dh2^T a1; dz1 = (dh2 W2) * dropout * relu'(bn1(h1)) in registers, its statistics ----
+  {
+    {
+      // dW2[j][k]: 4 x 4 register tile, k = lane + 32 i (consecutive lanes read consecutive rows: conflict-free with the
+      // padded pitch), j = 4 jg + jj (broadcast loads)
+      const int lane = tid & 31, jg = tid >> 5;
+      float acc[4][4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[jj][i] = 0.f;
+#pragma unroll 2
+      for (int q = 0; q < SB / 4; ++q) {
+        float4 av[4], dv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(a1T + (lane + 32 * i) * SP + q * 4);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) dv[jj] = *reinterpret_cast<const float4*>(a2T + (jg * 4 + jj) * SP + q * 4);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            acc[jj][i] = fmaf(av[i].x, dv[jj].x, fmaf(av[i].y, dv[jj].y, fmaf(av[i].z, dv[jj].z, fmaf(av[i].w, dv[jj].w, acc[jj][i]))));
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gp[a.off[4] + (jg * 4 + jj) * H1 + lane + 32 * i] = acc[jj][i];
+    }
+    const int j0 = (tid & 63) * 2, rg = tid >> 6, r0 = rg * 8;
+    float d[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { d[i][0] = 0.f; d[i][1] = 0.f; }
+#pragma unroll 4
+    for (int j = 0; j < H2; ++j) {
+      const float4 x0 = *reinterpret_cast<const float4*>(a2T + j * SP + r0), x1 = *reinterpret_cast<const float4*>(a2T + j * SP + r0 + 4);
+      const float w0 = W2s[j0 * LW2 + j], w1 = W2s[(j0 + 1) * LW2 + j];
+      fma2s(d[0][0], d[0][1], x0.x, w0, w1); fma2s(d[1][0], d[1][1], x0.y, w0, w1);
+      fma2s(d[2][0], d[2][1], x0.z, w0, w1); fma2s(d[3][0], d[3][1], x0.w, w0, w1);
+      fma2s(d[4][0], d[4][1], x1.x, w0, w1); fma2s(d[5][0], d[5][1], x1.y, w0, w1);
+      fma2s(d[6][0], d[6][1], x1.z, w0, w1); fma2s(d[7][0], d[7][1], x1.w, w0, w1);
+    }
+    float xh[8][2];
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = j0 + c;
+      const float sc = c1[j], sh = c1[H1 + j], mean = c1[2 * H1 + j], rstd = c1[3 * H1 + j];
+      const float4 h0 = *reinterpret_cast<const float4*>(h1T + j * SP + r0), h1v = *reinterpret_cast<const float4*>(h1T + j * SP + r0 + 4);
+      const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1v.x, h1v.y, h1v.z, h1v.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        float t = d[i][c];
+        if (drop) t = (hash_u32(seed, r, j) * (1.0f / 4294967296.0f)) >= a.p ? t * keep_scale : 0.f;
+        t = (r < B && fmaf(hv[i], sc, sh) > 0.f) ? t : 0.f;
+        d[i][c] = t;
+        xh[i][c] = (hv[i] - mean) * rstd;
+        s1[c] += t; s2[c] += t * xh[i][c];
+      }
+    }
+    part[(rg * 2 + 0) * H1 + j0] = s1[0]; part[(rg * 2 + 0) * H1 + j0 + 1] = s1[1];
+    part[(rg * 2 + 1) * H1 + j0] = s2[0]; part[(rg * 2 + 1) * H1 + j0 + 1] = s2[1];
+    __syncthreads();                                         // dW2 has read a1T; the partials are in
+    if (tid < H1) {
+      double S1 = 0.0, S2 = 0.0;
+      for (int g = 0; g < 8; ++g) { S1 += (double)part[(g * 2 + 0) * H1 + tid]; S2 += (double)part[(g * 2 + 1) * H1 + tid]; }
+      const double rstd = c1[3 * H1 + tid];
+      const double A = (double)g1[tid] * rstd, Bc = -A * rstd * S2 / B, Cc = -A * S1 / B;
+      c1[4 * H1 + tid] = (float)A; c1[5 * H1 + tid] = (float)Bc; c1[6 * H1 + tid] = (float)Cc;
+      gp[a.off[2] + tid] = (float)S2; gp[a.off[3] + tid] = (float)S1; gp[a.off[1] + tid] = 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = j0 + c;
+      const float A = c1[4 * H1 + j], Bc = c1[5 * H1 + j], Cc = c1[6 * H1 + j], rinv = 1.f / c1[3 * H1 + j];
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = r0 + i < B ? fmaf(A, d[i][c], fmaf(Bc, xh[i][c] * rinv, Cc)) : 0.f;
+      *reinterpret_cast<float4*>(a1T + j * SP + r0) = make_float4(o[0], o[1], o[2], o[3]);                   // dh1^T
+      *reinterpret_cast<float4*>(a1T + j * SP + r0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    __syncthreads();
+  }
+  MLP_TR();
+  // ---- dW1 = dh1^T x ----
+  {
+    // dW1[j][k]: 4 x 4 register tile, j = lane + 32 i, k = 4 kg + kk (threads whose k group lies behind D idle)
+    const int lane = tid & 31, kg = tid >> 5;
+    if (kg * 4 < D) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) acc[i][kk] = 0.f;
+#pragma unroll 2
+      for (int q = 0; q < SB / 4; ++q) {
+        float4 dv[4], xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dv[i] = *reinterpret_cast<const float4*>(a1T + (lane + 32 * i) * SP + q * 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) xv[kk] = *reinterpret_cast<const float4*>(xT + (kg * 4 + kk) * SP + q * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            acc[i][kk] = fmaf(dv[i].x, xv[kk].x, fmaf(dv[i].y, xv[kk].y, fmaf(dv[i].z, xv[kk].z, fmaf(dv[i].w, xv[kk].w, acc[i][kk]))));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(gp + a.off[0] + (size_t)(lane + 32 * i) * D + kg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+  }
+  MLP_TR();
+#ifdef AE_TRACE
+  if (tid == 0 && a.cursor == nullptr && (a.seed_dev == nullptr || (a.seed_dev[0] & 0xff) == 0x15))
+    printf("k_mlp_small clk: stage %lld  L1 %lld  L2 %lld  L3+CE %lld  bwd3 %lld  bwd2 %lld  bwd1 %lld\n", tr_t[1] - tr_t[0], tr_t[2] - tr_t[1],
+           tr_t[3] - tr_t[2], tr_t[4] - tr_t[3], tr_t[5] - tr_t[4], tr_t[6] - tr_t[5], tr_t[7] - tr_t[6]);
+#endif
+  if (tid == 0) {
+    if (a.seed_dev) a.seed_dev[0] += 0x9E3779B97F4A7C15ull;
+    if (a.nbt) { a.nbt[0] += 1; a.nbt[1] += 1; }
+    if (a.cursor) {
+      if (a.hist) { a.hist[2 * a.cursor[1]] = a.loss[0]; a.hist[2 * a.cursor[1] + 1] = (float)a.correct[0]; }
+      a.cursor[0] += B; a.cursor[1] += 1;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // Inference (NB:3499, NB:3702): running statistics, no dropout.  No cross-row dependency, so the grid
 // is one CTA per SM looping over 32-row chunks with the weights resident in shared memory.
 // ---------------------------------------------------------------------------------------------
@@ -705,7 +1138,21 @@ static int mlp_launch(MlpArgs& a, cudaStream_t st) {
   // step replayed as a graph: 148 / 101 / 97 / 97 us with 1 / 2 / 4 / 8 CTAs -- one CTA is bound by arithmetic (256 threads),
   // from 4 CTAs up by the cluster-wide exchanges.
   int nc = a.B >= 48 ? 8 : a.B >= 24 ? 4 : a.B >= 12 ? 2 : 1;
-  if (const char* ev = getenv("AE_B200_MLP_CLUSTER")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8) nc = v; }
+  const char* ev = getenv("AE_B200_MLP_CLUSTER");
+  if (ev) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8) nc = v; else ev = nullptr; }
+  // the whole fused training step of a batch of at most 64 rows: one CTA, everything in shared memory (k_mlp_small);
+  // AE_B200_MLP_CLUSTER=1/2/4/8 forces the cluster kernel (measurements, tests of every cluster size)
+  if (!ev && a.B <= SB && a.flags == (MLP_FWD | MLP_TRAIN | MLP_CE | MLP_BWD) && !a.keep_in && !a.dlogits_in && a.labels && a.grads &&
+      a.loss && a.correct) {
+    static bool small_attr = false;
+    if (!small_attr) {
+      AE_CUDA(cudaFuncSetAttribute(k_mlp_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMALL_SMEM));
+      small_attr = true;
+    }
+    k_mlp_small<<<1, NTS, MLP_SMALL_SMEM, st>>>(a);
+    AE_LAUNCH_CHECK();
+    return 0;
+  }
   switch (nc) {
     case 1: return mlp_launch_n<1>(a, st);
     case 2: return mlp_launch_n<2>(a, st);
