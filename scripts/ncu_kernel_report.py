@@ -39,7 +39,12 @@ def main(path, top=12):
             continue
         sh = src[1]
         ci = {h: i for i, h in enumerate(sh)}
-        data = [x for x in src[2:] if len(x) >= len(sh) - 2 and x[0] not in ("Kernel Name", "Address")]
+        data = []
+        for x in src[2:]:
+            if x and x[0] == "Kernel Name":                 # the next launch's section
+                break
+            if len(x) >= len(sh) - 2 and x[0] != "Address":
+                data.append(x)
         tot = sum(int(x[ci["# Samples"]]) for x in data) or 1
         print(f"   {len(data)} instructions, {tot} samples; most-sampled:")
         for x in sorted(data, key=lambda x: -int(x[ci["# Samples"]]))[:top]:
