@@ -521,9 +521,9 @@ def dp_gradient_check(dev, world, rank, comm, model, opt, stepper, xs_d, ys_d):
         v = v0 * b2 + g_ref * g_ref * (1 - b2)
         denom = v.sqrt() / (1 - b2 ** t) ** 0.5 + group["eps"]
         p_pred = p0 - (group["lr"] / (1 - b1 ** t)) * (m / denom)
-        # fused path: every rank keeps Adam's moments of its own 1/world shard only -- rank 0 can predict its shard
-        # (the first 864 elements, conv1.weight, are an exchange round of their own: rank 0's shard of the rest follows them)
-        own = slice(864, 864 + (((flat.len - 864) // 4 + world - 1) // world) * 4) if fused else slice(0, flat.len)
+        # fused path: every rank keeps Adam's moments of its own 1/world shard only -- rank 0 can predict its shard, the first
+        # ceil(len/4 / world) float4s of the flat buffer (dp.cu dp_adam_fused: ONE exchange round over the whole buffer)
+        own = slice(0, min(flat.len, ((flat.len // 4 + world - 1) // world) * 4)) if fused else slice(0, flat.len)
         upd_rel = float((p1[own] - p_pred[own]).norm() / (p_pred[own] - p0[own]).norm())
         # the same prediction with the SUM instead of the mean: how far off a missing 1/world would be
         ms_, vs_ = m0 + (g_ref * world - m0) * (1 - b1), v0 * b2 + (g_ref * world) ** 2 * (1 - b2)
