@@ -159,18 +159,6 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
     for (int w = 0; w < 16; ++w) mbar_init(ybar(w), 1);
     fence_barrier_init();
   }
-  for (int c = tid; c < MAXN; c += R2_THREADS) { sStat[0][c] = 0.f; sStat[1][c] = 0.f; }
-  for (int c = tid; c < q.N; c += R2_THREADS) {              // q.N <= MAXN output channels
-    float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q.epi.mode == AE_EPI_RELUBWD_STATS) {
-      const int ch = c % q.epi.C;
-      k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
-                      __ldg(q.epi.bnc + AE_BNC_MEAN * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_RSTD * q.epi.C + ch));
-    } else if (q.epi.bias) {
-      k.x = __ldg(q.epi.bias + c);
-    }
-    *reinterpret_cast<float4*>(&sCoef[c][0]) = k;
-  }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -338,6 +326,21 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
     // ===================== epilogue (warps 2..9; warp w reads TMEM lanes 32*(w%4) ..) =====================
     const int ew = warp - 2, qd = warp & 3, h = ew >> 2;
     const int et = tid - 64;
+    // per-channel coefficients and the statistics accumulators are epilogue-only state: loaded here, behind the CTA-wide
+    // barrier, so the producer's first copies do not wait for these global loads
+    for (int c = et; c < MAXN; c += 256) { sStat[0][c] = 0.f; sStat[1][c] = 0.f; }
+    for (int c = et; c < q.N; c += 256) {              // q.N <= MAXN output channels
+      float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q.epi.mode == AE_EPI_RELUBWD_STATS) {
+        const int ch = c % q.epi.C;
+        k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
+                        __ldg(q.epi.bnc + AE_BNC_MEAN * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_RSTD * q.epi.C + ch));
+      } else if (q.epi.bias) {
+        k.x = __ldg(q.epi.bias + c);
+      }
+      *reinterpret_cast<float4*>(&sCoef[c][0]) = k;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const Epilogue e = q.epi;
     const bool relubwd = e.mode == AE_EPI_RELUBWD_STATS;
     const bool do_stats = e.mode != AE_EPI_STORE && e.stats != nullptr;
