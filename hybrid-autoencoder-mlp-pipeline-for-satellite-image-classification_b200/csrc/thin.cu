@@ -44,11 +44,33 @@ __global__ void __launch_bounds__(TT_THREADS, WGRAD ? (GATHER ? 3 : 2) : 4) k_th
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(&bars[0]);
 
+  const int tiles = batch * TILES_PER_IMAGE;
+  // one thread: fetch the raw data of `tile` into stage st
+  auto issue = [&](int tile, int st) {
+    const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;
+    const uint32_t bar = bar0 + 8u * st;
+    float* base = stage0 + st * L.floats;
+    const int nsrc = thin.mode != AE_OP_RAW ? 2 : 1;
+    uint32_t bytes = (uint32_t)(XS_BYTES * nsrc);           // a box always delivers all its bytes (zeros where out of bounds)
+    if (WGRAD) bytes += WT_BYTES * (wide.mode == AE_OP_BNBWD ? 2 : 1);
+    mbar_arrive_expect_tx(bar, bytes);
+    // thin rows 8*tr-1 .. 8*tr+7, columns -4 .. 67: column c lands at index c + 4 of its XS_PITCH-wide row
+    tma_load_4d(smem_u32(base), &xmap, -4, 2 * TILE_ROWS * tr - 1, 0, n, bar);
+    if (nsrc == 2) tma_load_4d(smem_u32(base + L.xs2), &xmap2, -4, 2 * TILE_ROWS * tr - 1, 0, n, bar);
+    if (WGRAD) {
+      const size_t m0 = ((size_t)n * WH + tr * TILE_ROWS) * WW;
+      bulk_copy_g2s(smem_u32(base + L.wide), wide.src + m0 * WC, WT_BYTES, bar);
+      if (wide.mode == AE_OP_BNBWD) bulk_copy_g2s(smem_u32(base + L.wide2), wide.src2 + m0 * WC, WT_BYTES, bar);
+    }
+  };
+
   if (tid == 0) {
     tma_prefetch_desc(&xmap);
     if (thin.mode != AE_OP_RAW) tma_prefetch_desc(&xmap2);
     mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
     fence_barrier_init();
+    // the first tile's data is on its way while the CTA stages the weights and coefficients below
+    if ((int)blockIdx.x < tiles) issue(blockIdx.x, 0);
   }
   if (GATHER) {
     for (int i = tid; i < 27 * 32; i += TT_THREADS) {
@@ -102,27 +124,6 @@ __global__ void __launch_bounds__(TT_THREADS, WGRAD ? (GATHER ? 3 : 2) : 4) k_th
   }
   __syncthreads();
 
-  const int tiles = batch * TILES_PER_IMAGE;
-  // one thread: fetch the raw data of `tile` into stage st
-  auto issue = [&](int tile, int st) {
-    const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;
-    const uint32_t bar = bar0 + 8u * st;
-    float* base = stage0 + st * L.floats;
-    const int nsrc = thin.mode != AE_OP_RAW ? 2 : 1;
-    uint32_t bytes = (uint32_t)(XS_BYTES * nsrc);           // a box always delivers all its bytes (zeros where out of bounds)
-    if (WGRAD) bytes += WT_BYTES * (wide.mode == AE_OP_BNBWD ? 2 : 1);
-    mbar_arrive_expect_tx(bar, bytes);
-    // thin rows 8*tr-1 .. 8*tr+7, columns -4 .. 67: column c lands at index c + 4 of its XS_PITCH-wide row
-    tma_load_4d(smem_u32(base), &xmap, -4, 2 * TILE_ROWS * tr - 1, 0, n, bar);
-    if (nsrc == 2) tma_load_4d(smem_u32(base + L.xs2), &xmap2, -4, 2 * TILE_ROWS * tr - 1, 0, n, bar);
-    if (WGRAD) {
-      const size_t m0 = ((size_t)n * WH + tr * TILE_ROWS) * WW;
-      bulk_copy_g2s(smem_u32(base + L.wide), wide.src + m0 * WC, WT_BYTES, bar);
-      if (wide.mode == AE_OP_BNBWD) bulk_copy_g2s(smem_u32(base + L.wide2), wide.src2 + m0 * WC, WT_BYTES, bar);
-    }
-  };
-
-  if (tid == 0 && (int)blockIdx.x < tiles) issue(blockIdx.x, 0);
   int it = 0;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
     const int st = it & 1;
@@ -518,19 +519,6 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin_scatter_sigmoid(Operand 
   __shared__ float red[TT_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = smem_u32(&bar_raw), barx = smem_u32(&bar_x);
-  if (tid == 0) {
-    if (x) tma_prefetch_desc(&tmap);
-    mbar_init(bar, 1); mbar_init(barx, 1);
-    fence_barrier_init();
-  }
-  for (int o = tid; o < 27 * 32; o += TT_THREADS) {     // o = (tap*3 + co)*32 + ci  <-  w[ci][co][tap]
-    const int ci = o & 31, r = o >> 5, tap = r / 3, co = r - tap * 3;
-    Wsm[o] = __ldg(w + ci * 27 + co * 9 + tap);
-  }
-  if (tid < 64)
-    sbn[tid] = wide.mode == AE_OP_BNRELU ? __ldg(wide.bnc + (tid >> 5 ? AE_BNC_SHIFT : AE_BNC_SCALE) * WC + lane) : (tid >> 5 ? 0.f : 1.f);
-  const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
-  float err = 0.f;
   const int tiles = batch * TILES_PER_IMAGE;
   constexpr int UNITS = AS_ROWS * AS_COLS * 8;
   // one thread: fetch the raw rows of `tile` (the image's last tile has no halo row below it)
@@ -540,8 +528,21 @@ __global__ void __launch_bounds__(TT_THREADS, 4) k_thin_scatter_sigmoid(Operand 
     mbar_arrive_expect_tx(bar, bytes);
     bulk_copy_g2s(smem_u32(raw), wide.src + ((size_t)n * WH + tr * TILE_ROWS) * WW * WC, bytes, bar);
   };
+  if (tid == 0) {
+    if (x) tma_prefetch_desc(&tmap);
+    mbar_init(bar, 1); mbar_init(barx, 1);
+    fence_barrier_init();
+    if ((int)blockIdx.x < tiles) issue(blockIdx.x);     // on its way while the weights are staged
+  }
+  for (int o = tid; o < 27 * 32; o += TT_THREADS) {     // o = (tap*3 + co)*32 + ci  <-  w[ci][co][tap]
+    const int ci = o & 31, r = o >> 5, tap = r / 3, co = r - tap * 3;
+    Wsm[o] = __ldg(w + ci * 27 + co * 9 + tap);
+  }
+  if (tid < 64)
+    sbn[tid] = wide.mode == AE_OP_BNRELU ? __ldg(wide.bnc + (tid >> 5 ? AE_BNC_SHIFT : AE_BNC_SCALE) * WC + lane) : (tid >> 5 ? 0.f : 1.f);
+  const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+  float err = 0.f;
   __syncthreads();
-  if (tid == 0 && (int)blockIdx.x < tiles) issue(blockIdx.x);
   int it = 0;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
     const int n = tile / TILES_PER_IMAGE, tr = tile - n * TILES_PER_IMAGE;

@@ -241,22 +241,6 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     fence_barrier_init();
   }
-  for (int c = tid; c < 256; c += RG_THREADS) { sStat[0][c] = 0.f; sStat[1][c] = 0.f; }
-  for (int c = tid; c < q.N; c += RG_THREADS) {              // q.N <= 256 output channels
-    float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q.epi.mode == AE_EPI_RELUBWD_STATS) {
-      const int ch = c % q.epi.C;
-      k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
-                      __ldg(q.epi.bnc + AE_BNC_MEAN * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_RSTD * q.epi.C + ch));
-    } else if (q.epi.mode == AE_EPI_BNRELU_SPLIT) {           // relu(scale*(acc + bias) + shift), rounded exactly as the two-pass form
-      const int ch = c % q.epi.C;
-      k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
-                      q.epi.bias ? __ldg(q.epi.bias + c) : 0.f, 0.f);
-    } else if (q.epi.bias) {
-      k.x = __ldg(q.epi.bias + c);
-    }
-    *reinterpret_cast<float4*>(&sCoef[c][0]) = k;
-  }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -375,6 +359,25 @@ __global__ void __launch_bounds__(RG_THREADS) k_tma_rowgemm(const __grid_constan
     __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5; warp w owns TMEM lanes 32*(w%4) ..) =====================
+    // epilogue-only state (statistics accumulators, per-channel coefficients): loaded behind the CTA-wide barrier so that the
+    // producer's first copies do not wait for these global loads; bar 1 = the four epilogue warps
+    for (int c = tid - 64; c < 256; c += 128) { sStat[0][c] = 0.f; sStat[1][c] = 0.f; }
+    for (int c = tid - 64; c < q.N; c += 128) {              // q.N <= 256 output channels
+      float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q.epi.mode == AE_EPI_RELUBWD_STATS) {
+        const int ch = c % q.epi.C;
+        k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
+                        __ldg(q.epi.bnc + AE_BNC_MEAN * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_RSTD * q.epi.C + ch));
+      } else if (q.epi.mode == AE_EPI_BNRELU_SPLIT) {           // relu(scale*(acc + bias) + shift), rounded exactly as the two-pass form
+        const int ch = c % q.epi.C;
+        k = make_float4(__ldg(q.epi.bnc + AE_BNC_SCALE * q.epi.C + ch), __ldg(q.epi.bnc + AE_BNC_SHIFT * q.epi.C + ch),
+                        q.epi.bias ? __ldg(q.epi.bias + c) : 0.f, 0.f);
+      } else if (q.epi.bias) {
+        k.x = __ldg(q.epi.bias + c);
+      }
+      *reinterpret_cast<float4*>(&sCoef[c][0]) = k;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const int et = tid - 64;
