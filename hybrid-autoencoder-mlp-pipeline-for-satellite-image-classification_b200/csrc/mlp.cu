@@ -1054,9 +1054,19 @@ __global__ void __launch_bounds__(NT, 1) k_mlp_eval(const float* __restrict__ pa
   const int nchunks = (B + CHUNK - 1) / CHUNK;
   for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const int c0 = ch * CHUNK, nv = min(CHUNK, B - c0);
-    for (int i = tid; i < D * CHUNK; i += NT) {
-      const int r = i / D, k = i - r * D;
-      stgA[k * CHUNK + r] = r < nv ? __ldg(x + (size_t)(c0 + r) * D + k) : 0.f;
+    {
+      // the chunk's rows: all of a thread's global loads first (8 x 256 = D * CHUNK at D = 64), then the transposing stores
+      float xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = tid + u * NT, r = i / D, k = i - r * D;
+        xv[u] = (i < D * CHUNK && r < nv) ? __ldg(x + (size_t)(c0 + r) * D + k) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = tid + u * NT, r = i / D, k = i - r * D;
+        if (i < D * CHUNK) stgA[k * CHUNK + r] = xv[u];
+      }
     }
     __syncthreads();
     tile_linear_act<H1>(stgA, D, W1s, LD1, b1, cf, cf + H1, stgB);

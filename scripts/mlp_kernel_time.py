@@ -17,3 +17,15 @@ for batch in ([int(a) for a in sys.argv[1:]] or [64]):
     for _ in range(500): step.run()
     e1.record(); torch.cuda.synchronize()
     print(f"batch {batch}: {e0.elapsed_time(e1) / 500 * 1e3:.1f} us per replayed step (AE_B200_MLP_CLUSTER={os.environ.get('AE_B200_MLP_CLUSTER', 'auto')})")
+
+# eval: k_mlp_eval on 4096 latents (part of the inference pass)
+clf = ae_b200.MLP(64, 10).to(dev).eval()
+X = torch.randn(4096, 64, device=dev)
+with torch.no_grad():
+    for _ in range(10): clf.predict(X)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200): clf.predict(X)
+    e1.record(); torch.cuda.synchronize()
+print(f"MLP eval, 4096 rows: {e0.elapsed_time(e1) / 200 * 1e3:.1f} us per call (host loop included)")
