@@ -91,9 +91,10 @@ def fit_autoencoder(model, optimizer, train_loader: DeviceLoader, val_loader: De
 def train_epoch_mlp(clf, optimizer, X: torch.Tensor, y: torch.Tensor, batch_size: int = 64, shuffle: bool = True,
                     generator: Optional[torch.Generator] = None):
     """NB:3471-3489 over latents X [N,D] / labels y [N] that already live on the device (the reference wraps the CPU
-    copies in a TensorDataset, NB:3443).  Per batch: ONE replay of a captured two-launch graph (cluster kernel: forward + CE
-    + backward; fused flat Adam) on a batch gathered into its input buffers; the losses and correct counts stay in a
-    device history and are read once.  Returns (train_loss, train_acc)."""
+    copies in a TensorDataset, NB:3443).  Per batch: ONE replay of a captured two-launch graph (forward + CE + backward in
+    one kernel -- one CTA with everything in shared memory up to 64 rows, a cluster above that -- and the fused flat Adam)
+    that reads its rows through the epoch's permutation and records loss / correct count in a device history itself
+    (`ae_mlp_train_step_indexed`); the history is read once per epoch.  Returns (train_loss, train_acc)."""
     from .train import MLPTrainStep
     clf.train()
     n, dev = int(X.shape[0]), X.device

@@ -190,8 +190,9 @@ class TrainStep:
 
 class MLPTrainStep:
     """One MLP training step of the reference loop (NB:3476-3482: zero_grad, forward, cross-entropy, backward,
-    Adam.step) captured ONCE as a CUDA graph of two launches -- the cluster kernel (forward + BatchNorm1d + dropout + CE +
-    backward) and the fused flat Adam -- on fixed device buffers.  Nothing that changes between steps is baked in: the
+    Adam.step) captured ONCE as a CUDA graph of two launches -- forward + BatchNorm1d + dropout + CE + backward in one kernel
+    (one CTA with every intermediate in shared memory for batches up to 64 rows, a thread-block cluster above that) and the
+    fused flat Adam -- on fixed device buffers.  Nothing that changes between steps is baked in: the
     dropout seed advances on the device.  `load` copies / gathers a batch into the buffers, `run` replays."""
 
     def __init__(self, clf, optimizer: Adam, batch: int, device=None, epoch=None):
