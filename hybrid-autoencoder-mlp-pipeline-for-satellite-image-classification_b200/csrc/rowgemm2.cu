@@ -168,9 +168,10 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_rowgemm2(const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
-    // Measured (scripts/trace_rowgemm.py): what bounds this thread is the issue of the copies themselves (~100 clk per
-    // cp.async.bulk / tensor load, a 256-row activation box keeps the TMA unit busy ~500 clk), not address arithmetic;
-    // spreading the weight-plane copies over the lanes of the warp was tried and is slower.
+    // Measured (scripts/trace_rowgemm.py): ~100 clk per cp.async.bulk / tensor load, a 256-row activation
+    // box keeps the TMA unit busy ~500 clk.  Neither the number of copies (group pack: one per weight group), the ring depth
+    // nor the order of the K chunks changes the kernel's time: this thread is not what paces the main loop.  Spreading the
+    // weight-plane copies over the lanes of the warp was tried and is slower.
     if (lane == 0) {
       const int P = g.Hs * g.Ws;
       // ring positions advance incrementally: this is one thread, every integer division would be on the critical path
