@@ -39,20 +39,6 @@ __global__ void __launch_bounds__(256) k_split_operand(Operand op, int64_t n8, i
                                                       __nv_bfloat16* __restrict__ dst, BnJob job) {
   __shared__ __align__(16) float sc[4][256];             // BNRELU: scale, shift.  BNBWD: A, B, C, mean
   const int C = op.C;
-  // the first chunk's loads are issued BEFORE the coefficient prologue (global loads of the fp64 sums, fp64 division / square
-  // root, a barrier): the two latencies overlap instead of adding up -- most launches are a single chunk per thread
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float4 a0, a1, y0, y1;
-  a0 = a1 = y0 = y1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < n8) {
-    a0 = __ldg(reinterpret_cast<const float4*>(op.src + (size_t)i * 8));
-    a1 = __ldg(reinterpret_cast<const float4*>(op.src + (size_t)i * 8) + 1);
-    if (op.mode == AE_OP_BNBWD) {
-      y0 = __ldg(reinterpret_cast<const float4*>(op.src2 + (size_t)i * 8));
-      y1 = __ldg(reinterpret_cast<const float4*>(op.src2 + (size_t)i * 8) + 1);
-    }
-  }
   if (op.mode != AE_OP_RAW) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       if (job.kind == BN_JOB_FINALIZE) {
@@ -100,25 +86,20 @@ __global__ void __launch_bounds__(256) k_split_operand(Operand op, int64_t n8, i
     }
     __syncthreads();
   }
-  for (; i < n8; i += stride) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const size_t off = (size_t)i * 8;
     const int c = (int)(off % (size_t)C);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(op.src + off));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(op.src + off) + 1);
     float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-    if (i + stride < n8) {                                 // the next chunk's loads, in flight while this one is converted
-      const size_t nx = (size_t)(i + stride) * 8;
-      a0 = __ldg(reinterpret_cast<const float4*>(op.src + nx));
-      a1 = __ldg(reinterpret_cast<const float4*>(op.src + nx) + 1);
-      if (op.mode == AE_OP_BNBWD) {
-        y0 = __ldg(reinterpret_cast<const float4*>(op.src2 + nx));
-        y1 = __ldg(reinterpret_cast<const float4*>(op.src2 + nx) + 1);
-      }
-    }
     if (op.mode == AE_OP_BNRELU) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[0][c + j], sc[1][c + j]), 0.f);
     } else if (op.mode == AE_OP_BNBWD) {
       // dy = A*dz + B*(y - mean) + C, (y - mean) formed first (same order as load_operand4)
+      const float4 y0 = __ldg(reinterpret_cast<const float4*>(op.src2 + off));
+      const float4 y1 = __ldg(reinterpret_cast<const float4*>(op.src2 + off) + 1);
+      const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(sc[0][c + j], v[j], fmaf(sc[1][c + j], y[j] - sc[3][c + j], sc[2][c + j]));
     }
