@@ -663,6 +663,16 @@ __global__ void __launch_bounds__(NTS, 1) k_mlp_small(MlpArgs a) {
     part[(rg * 2 + 0) * H1 + j0] = s1[0]; part[(rg * 2 + 0) * H1 + j0 + 1] = s1[1];
     part[(rg * 2 + 1) * H1 + j0] = s2[0]; part[(rg * 2 + 1) * H1 + j0 + 1] = s2[1];
     __syncthreads();
+    // layer 1's weights are not needed again: their space takes W2 in its natural [j][k] orientation (pitch LW1), which the
+    // backward pass reads as conflict-free 8-byte pairs (W2s[k][j] with k = 2 * lane is a 4-way bank conflict there)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i4 = tid + u * NTS;                         // 2048 float4 = 64 x 128
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(W2) + i4);
+      const int j = i4 >> 5, k = (i4 & 31) * 4;
+      *reinterpret_cast<float2*>(W1s + j * LW1 + k) = make_float2(wv.x, wv.y);
+      *reinterpret_cast<float2*>(W1s + j * LW1 + k + 2) = make_float2(wv.z, wv.w);
+    }
     if (tid < H1) {
       double S1 = 0.0, S2 = 0.0;
       for (int g = 0; g < 8; ++g) { S1 += (double)part[(g * 2 + 0) * H1 + tid]; S2 += (double)part[(g * 2 + 1) * H1 + tid]; }
@@ -895,7 +905,8 @@ __global__ void __launch_bounds__(NTS, 1) k_mlp_small(MlpArgs a) {
 #pragma unroll 4
     for (int j = 0; j < H2; ++j) {
       const float4 x0 = *reinterpret_cast<const float4*>(a2T + j * SP + r0), x1 = *reinterpret_cast<const float4*>(a2T + j * SP + r0 + 4);
-      const float w0 = W2s[j0 * LW2 + j], w1 = W2s[(j0 + 1) * LW2 + j];
+      const float2 w01 = *reinterpret_cast<const float2*>(W1s + j * LW1 + j0);   // W2[j][j0], W2[j][j0 + 1]
+      const float w0 = w01.x, w1 = w01.y;
       fma2s(d[0][0], d[0][1], x0.x, w0, w1); fma2s(d[1][0], d[1][1], x0.y, w0, w1);
       fma2s(d[2][0], d[2][1], x0.z, w0, w1); fma2s(d[3][0], d[3][1], x0.w, w0, w1);
       fma2s(d[4][0], d[4][1], x1.x, w0, w1); fma2s(d[5][0], d[5][1], x1.y, w0, w1);
